@@ -1,0 +1,5 @@
+// TEST INFRASTRUCTURE ONLY (oracle): forwards to the DSPONE/WIPP stand-in.
+#ifndef FWD_WIPP_WIPPSTATS_H
+#define FWD_WIPP_WIPPSTATS_H
+#include <wipp/wipp.h>
+#endif

@@ -1,0 +1,64 @@
+"""Generates tests/golden/*.npz from the REFERENCE BUILD (oracle/_ref/libmcarray_ref.so = the reference's
+own sources compiled in this container against the DSPONE/WIPP stand-in; `make -C oracle ref`).
+Run here (needs /root/reference):   python tests/golden/make_golden.py
+The fixtures are committed; on the GPU box the tests read them, never /root/reference."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle", "py"))
+import orc  # noqa: E402
+from mcarray_b200 import scenes  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    orc.build(ref=True)
+    assert orc.have_ref(), "reference build unavailable"
+    # 1. SourceSeparationAndLocalisation, Reem-C array (test_mcarray.cpp:397), 2 sources asked, 1 present
+    fs = 16000
+    xyz = scenes.linear_array([0, 0.07, 0.175, 0.21])
+    x = np.round(scenes.far_field_scene(xyz, fs, 6144, scenes.azimuth_dirs([np.deg2rad(30)]), seed=101))
+    r = orc.ssl_run(fs, xyz, 2, x, chunk=1000, want_corr=True, prefix="ref")
+    np.savez_compressed(os.path.join(HERE, "ssl_reemc_16k.npz"), fs=fs, xyz=xyz, S=2, x=x.astype(np.int16), chunk=1000,
+                        out=r["out"], doa_deg=r["doa_deg"], prob=r["prob"], power=r["power"], energy=r["energy"],
+                        corr_scaled=r["corr_scaled"], fired_frame=r["fired_frame"], N=r["N"])
+    # 2. mcbeam's own configuration (mcabeamf.cpp:182-194), 48 kHz -> N = 2048
+    fs = 48000
+    xyz = scenes.linear_array([-2.25, -1.25, 1.25, 2.25])
+    x = np.round(scenes.far_field_scene(xyz, fs, 5 * 2048, scenes.azimuth_dirs([np.deg2rad(-20)]), seed=102))
+    r = orc.ssl_run(fs, xyz, 1, x, chunk=1024, prefix="ref")
+    np.savez_compressed(os.path.join(HERE, "ssl_mcbeam_48k.npz"), fs=fs, xyz=xyz, S=1, x=x.astype(np.int16), chunk=1024,
+                        out=r["out"][:1], doa_deg=r["doa_deg"], prob=r["prob"], power=r["power"], energy=r["energy"],
+                        fired_frame=r["fired_frame"], N=r["N"])
+    # 3. FreqGCCBinauralLocalisation, 0.086 m (test_mcarray.cpp:284)
+    fs = 16000
+    xyz = scenes.linear_array([0, 0.086])
+    x = np.round(scenes.far_field_scene(xyz, fs, 10 * 1024, scenes.azimuth_dirs([np.deg2rad(-21)]), seed=103))
+    r = orc.freqgcc_run(fs, 0.086, x, chunk=2048, prefix="ref")
+    np.savez_compressed(os.path.join(HERE, "freqgcc_16k.npz"), fs=fs, mic_dist=0.086, x=x.astype(np.int16), chunk=2048,
+                        curves=r["curves"], idx=r["idx"], power=r["power"], N=r["N"])
+    # 4. FastBinauralMasking on the reference's spatial-masking test signal (test_mcarray.cpp:908-929)
+    n = 5 * 1024
+    i = np.arange(n)
+    sig = np.round(5000 * np.cos(2 * np.pi * 0.1 * i)); inter = np.round(5000 * np.cos(2 * np.pi * 0.3 * i))
+    L = sig + inter; R = sig.copy(); R[: n - 6] += inter[6:]
+    x = np.stack([L, R])
+    fx = {}
+    for name, method in (("full", 3), ("relative", 1), ("factor", 0), ("noisy", 4)):
+        r = orc.mask_run(16000, 0.086, 500, 5000, method, 0, x, chunk=1000, want_spectra=True, prefix="ref")
+        fx[f"out_{name}"] = r["out"]; fx[f"Q_{name}"] = r["Q"]
+        if name == "relative":
+            fx["spectra_relative"] = r["spectra"]
+    np.savez_compressed(os.path.join(HERE, "mask_spatial_16k.npz"), fs=16000, mic_dist=0.086, lo=500.0, hi=5000.0,
+                        x=x.astype(np.int16), chunk=1000, N=r["N"], **fx)
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()
