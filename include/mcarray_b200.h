@@ -1,0 +1,185 @@
+/* mcarray_b200 — C ABI of the B200 (sm_100a) implementation of mcarray's frame-based multichannel hot path.
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes, status codes instead of exceptions.  The C++
+ * classes under include/mcarray/ (same names and constructor signatures as the reference's include/mcarray/) are
+ * thin wrappers over it; INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * One processor handle <-> one CUDA device <-> one CUDA stream; handles are stateful and not re-entrant, exactly like
+ * the reference objects they replace (one object per array stream, no locks: SURVEY.md §8b "Threading").  A handle can
+ * carry B independent array streams that are processed in lock step (B = 1 reproduces one reference object).
+ *
+ * What each entry point replaces in the reference (/root/reference):
+ *   mcag_create / mcag_destroy        constructors / destructors of SourceSeparationAndLocalisation
+ *                                     (include/mcarray/SourceSeparationAndLocalisation.h:42-56), SourceLocalisation
+ *                                     (SourceLocalisation.h:38-52), FreqGCCBinauralLocalisation (BinauralLocalisation.h:188-192),
+ *                                     FastBinauralMasking (FastBinauralMasking.h:71-104)
+ *   mcag_process_f32/_f64/_s16        dsp::ShortTimeProcess::process(in, n, out, outsize) as called at
+ *                                     src/programs/mcabeamf.cpp:112 and test/test_mcarray.cpp:618,622,937,1023
+ *   mcag_get_info                     getFrameSize / getWindowSize / getAnalysisLength / getMaxLatency /
+ *                                     getNumberOfChannels (mcabeamf.cpp:85, test_mcarray.cpp:596,843-844,896)
+ *   mcag_fetch_*                      LocalisationCallback::setDOA deliveries (SoundLocalisationCallback.h:53;
+ *                                     BeamformingSeparationAndLocalisation.cpp:91-94, BinauralLocalisation.cpp:521)
+ *   mcag_k_*                          the per-frame algorithms themselves on device buffers:
+ *                                     SteeringBeamforming.cpp:96-195, Beamformer.cpp:51-71,
+ *                                     FastBinauralMasking.cpp:126-538, DSPONE's STFT and GeneralisedCrossCorrelation
+ */
+#ifndef MCARRAY_B200_H
+#define MCARRAY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mcag_proc_s *mcag_proc;
+
+enum {
+  MCAG_OK = 0,
+  MCAG_ERR_INVALID = 1,   /* bad argument / unsupported configuration (the C++ wrappers rethrow MCArrayException) */
+  MCAG_ERR_CUDA = 2,      /* CUDA runtime error; see mcag_last_error() */
+  MCAG_ERR_NOMEM = 3,
+  MCAG_ERR_CAPACITY = 4   /* more frames in one call than max_frames_per_call, or output buffer too small */
+};
+
+/* processor kinds */
+enum {
+  MCAG_KIND_SSL = 0,      /* SourceSeparationAndLocalisation: STFT -> SRP(GCC-PHAT, tau grid) -> selectDOA -> DS -> OLA */
+  MCAG_KIND_SL = 1,       /* SourceLocalisation: the same without separation / synthesis */
+  MCAG_KIND_FREQGCC = 2,  /* FreqGCCBinauralLocalisation: 2-mic GCC-PHAT curve, smoothing, argmax cell */
+  MCAG_KIND_MASK = 3,     /* FastBinauralMasking: STFT -> 45-band spatial/temporal mask -> OLA */
+  MCAG_KIND_TDOA = 4,     /* integer-lag GCC-PHAT on all pairs (BASELINE config 2) */
+  MCAG_KIND_DSFAN = 5,    /* delay-and-sum to a fan of D azimuths, spectra out (BASELINE config 3) */
+  MCAG_KIND_SRP = 6       /* SRP-PHAT map over a large grid, channel form (BASELINE config 4) */
+};
+
+/* result arrays (mcag_fetch_* / mcag_device_ptr); shapes use T = frames of the last process call */
+enum {
+  MCAG_OUT_SPECTRA = 0,   /* float2 [B][T][M][N/2+2]  analysis spectra (pad bin zero)            */
+  MCAG_OUT_POWER_DB = 1,  /* float  [B][T]            dsp::SignalPower::FFTLogPower of the frame  */
+  MCAG_OUT_CORR = 2,      /* float  [B][T][P][D]      Re GCC-PHAT per pair on the tau grid        */
+  MCAG_OUT_ENERGY = 3,    /* float  [B][T][D]         smoothed energy map (SSL/SL/SRP)            */
+  MCAG_OUT_CELL = 4,      /* int32  [B][T][S]         selected grid cells (SSL/SL), [B][T] (FREQGCC argmax, SRP argmax) */
+  MCAG_OUT_PROB = 5,      /* float  [B][T][S]         peak weights ("prob")                       */
+  MCAG_OUT_LAGS = 6,      /* int32  [B][T][P]         integer TDOA lags (TDOA)                    */
+  MCAG_OUT_CURVES = 7,    /* float  [B][T][P][2L+1] (TDOA) or [B][T][D] smoothed curve (FREQGCC)  */
+  MCAG_OUT_ACTIVE = 8,    /* uint8  [B][T]            1 where the power gate let the frame through */
+  MCAG_OUT_BEAMS = 9,     /* float2 [B][T][C][N/2+2]  beamformed / masked spectra (SSL, MASK, DSFAN: C = D) */
+  MCAG_OUT_MASK_Q = 10,   /* float  [B][T][nb]        short-time band power after each frame (MASK) */
+  MCAG_OUT_MASK_DEC = 11  /* uint8  [B][T][nb]        2 = spatial mask, 1 = temporal mask, 0 = pass (MASK) */
+};
+
+enum {                    /* emit flags: keep optional intermediates of the last call fetchable */
+  MCAG_EMIT_CORR = 1, MCAG_EMIT_CURVES = 2
+};
+
+typedef struct {
+  int kind;               /* MCAG_KIND_* */
+  int device;             /* CUDA device ordinal */
+  int sample_rate;
+  int frame_size;         /* N in {256, 512, 1024, 2048} */
+  int hop;                /* window shift; N/2 is the DSPONE convention */
+  int n_channels;         /* M microphones per array stream */
+  int n_streams;          /* B independent array streams processed in lock step */
+  int max_frames_per_call;/* workspace sizing: a process call may complete at most this many frames per stream */
+  const double *window;   /* [N] analysis = synthesis window, NULL = sqrt of the periodic Hann */
+  int emit;               /* MCAG_EMIT_* */
+
+  /* direction / delay grid */
+  int n_dirs;             /* D */
+  const double *pair_tau; /* [P][D] pair delays in samples, pairs i<j lexicographic (SSL, SL, FREQGCC) */
+  const double *mic_tau;  /* [M][D] per-microphone advances in samples (SRP channel form)              */
+  const double *steer_turns; /* [D][M] phase increment per bin in turns, Beamformer.cpp:59 / (2 pi) (SSL, DSFAN) */
+  int n_sources;          /* S */
+  float energy_memory;    /* 0.8f: SteeringBeamforming.h:70 */
+  float corr_memory;      /* 0.8f: BinauralLocalisation.h:198 */
+  int use_power_floor;    /* SoundLocalisationImpl power gate */
+  float noise_margin_db;  /* 3 (BeamformingSeparationAndLocalistaion.h:52) or 6 (BinauralLocalisation.h:197) */
+  float floor_seconds;    /* 3: SoundLocalisationImpl.h:77 */
+  int floor_ccs_power;    /* 0: FFTPower*(N) accumulation (BSAL.cpp:58); 1: mean-square of the CCS buffer + 1e-10 (BinauralLocalisation.cpp:390-391) */
+  int noise_preestimated; /* start with the floor already "estimated" at 0 (see oracle/CONVENTIONS.md) */
+
+  int max_lag;            /* TDOA: lags -max_lag..max_lag */
+
+  /* masking */
+  int mask_method;        /* FACTOR=0 RELATIVE=1 FULL=3 NOISY=4 NOTHING=5 (ArrayModules.h:81) */
+  int mask_alg;           /* BOTH=0 SPATIAL=1 TEMPORAL=2 (ArrayModules.h:89) */
+  int n_bands;            /* 45 (FastBinauralMasking.h:111) */
+  const double *band_coefs;      /* [n_bands][N/2+1] real filter-bank magnitudes */
+  const double *band_thresholds; /* [n_bands] cos(w_b d sin(phi)/c) (FastBinauralMasking.cpp:342-366) */
+} mcag_config;
+
+typedef struct {
+  int frame_size, window_size, hop, analysis_length, one_sided_length, n_channels, n_streams, max_latency;
+  int n_dirs, n_pairs, n_sources, n_out_channels, spectrum_pitch, max_frames_per_call;
+} mcag_info;
+
+const char *mcag_last_error(void);
+int mcag_version(void);
+
+void mcag_config_init(mcag_config *cfg);                 /* zero + reference defaults */
+int mcag_create(const mcag_config *cfg, mcag_proc *out);
+void mcag_destroy(mcag_proc p);
+int mcag_reset(mcag_proc p);                             /* back to the freshly-constructed state */
+int mcag_flush_input(mcag_proc p);                       /* drop buffered input samples (start of a new segment); host-only, no sync */
+int mcag_get_info(mcag_proc p, mcag_info *info);
+int mcag_synchronize(mcag_proc p);
+
+/* Streaming process.  `in` holds B*M planar host pointers (stream-major), nsamples each; `out` holds B*C planar host
+ * pointers with room for out_capacity samples each (C = n_out_channels; NULL for analysis-only kinds).  Returns the
+ * number of samples written per output channel in *nsamples_out (hop per completed frame); callers size the output as
+ * nsamples + max_latency like mcabeamf.cpp:85.  Synchronous: results are fetchable when it returns. */
+int mcag_process_f32(mcag_proc p, const float *const *in, int nsamples, float *const *out, int out_capacity, int *nsamples_out);
+int mcag_process_f64(mcag_proc p, const double *const *in, int nsamples, double *const *out, int out_capacity, int *nsamples_out);
+int mcag_process_s16(mcag_proc p, const int16_t *const *in, int nsamples, int16_t *const *out, int out_capacity, int *nsamples_out);
+/* Same with one contiguous host block per call: in [B*M][in_pitch], out [B*C][out_pitch] (pinned memory recommended). */
+int mcag_process_packed_f32(mcag_proc p, const float *in, long long in_pitch, int nsamples, float *out, long long out_pitch, int *nsamples_out);
+/* Device-resident variant: in / out are device pointers on the handle's device; asynchronous on the handle's stream. */
+int mcag_process_device_f32(mcag_proc p, const float *d_in, long long in_pitch, int nsamples, float *d_out, long long out_pitch, int *nsamples_out);
+
+int mcag_frames_done(mcag_proc p);                        /* frames per stream completed by the last process call */
+long long mcag_frames_total(mcag_proc p);                 /* since creation / reset */
+int mcag_fetch(mcag_proc p, int what, void *dst, long long bytes);   /* device -> host copy of a result array */
+const void *mcag_device_ptr(mcag_proc p, int what);      /* zero-copy access for device-side consumers */
+void *mcag_stream(mcag_proc p);                           /* cudaStream_t the handle launches on */
+long long mcag_kernel_launches(mcag_proc p);              /* kernels launched by this handle since creation */
+
+/* Pinned host memory helpers for the end-to-end path */
+void *mcag_host_alloc(long long bytes);
+void mcag_host_free(void *ptr);
+
+/* ---- kernel-level entry points on DEVICE buffers (what the processors are made of; also used by the parity tests) ----
+ * `stream` is a cudaStream_t (NULL = default stream).  Spectra rows have pitch N/2+2 complex bins. */
+int mcag_k_twiddles(int N, void *d_tw /* float2 [N/2] */, void *stream);
+int mcag_k_stft(const float *d_x, long long row_pitch, int rows, int M, int T, int N, int hop, const float *d_win, const void *d_tw,
+                void *d_spec, float *d_chan_pow, void *stream);
+int mcag_k_istft(const void *d_spec, int B, int T, int C_in, int C_out, int N, int hop, const float *d_win, const void *d_tw,
+                 const float *d_tail_in, float *d_tail_out, float *d_out, long long out_pitch, void *stream);
+int mcag_k_tdoa_lags(const void *d_spec, int B, int T, int M, int N, int max_lag, const void *d_tw, float *d_curves, int32_t *d_lags,
+                     float *d_peaks, void *stream);
+int mcag_k_phase_fx(const double *h_turns, long long n, uint64_t *d_fx, void *stream);   /* host turns -> device 0.64 fixed point */
+int mcag_k_gcc_tau(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_pair_fx, int D, float *d_corr, void *stream);
+int mcag_k_pair_sum(const float *d_corr, long long BT, int P, int D, float scale, float *d_esum, void *stream);
+int mcag_k_energy_scan(const float *d_esum, int B, int T, int D, float a, const unsigned char *d_active, float *d_state, float *d_energy, void *stream);
+int mcag_k_select_doa(const float *d_energy, long long BT, int D, int n_pairs, int S, int32_t *d_idx, float *d_prob, void *stream);
+int mcag_k_ds_fan(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_steer_fx, int D, void *d_out, void *stream);
+int mcag_k_srp_channel(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_mic_fx, int D, float *d_srp, void *stream);
+int mcag_k_srp_tensor(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_mic_fx, int D, float *d_srp, void *stream);
+
+/* ---- host-side constructor math of the reference processors (no GPU work; float typing as the reference helpers) ----
+ * microhponeArrayHelpers.cpp:38-72,110-120; SteeringBeamforming.cpp:34-94; Beamformer.cpp:59; FastBinauralMasking.cpp:342-366 */
+int mcag_geom_frame_size(int fs, double frame_rate);                       /* 2^calculateOrderFromSampleRate */
+int mcag_geom_grid_size(float doa_step);                                   /* round(pi/step)+1 */
+double mcag_geom_cell_angle(int idx, float doa_step);                      /* doaIdx2angle */
+int mcag_geom_pair_tau_reference(const double *mic_xyz, int M, int fs, float doa_step, double *tau /* [P][D] */);
+int mcag_geom_steer_turns_reference(const double *mic_xyz, int M, int fs, int N, float doa_step, double *turns /* [D+1][M] */);
+void mcag_geom_steer_turns(const double *mic_xyz, int M, int fs, int N, const double *doas, int D, double *turns /* [D][M] */);
+void mcag_geom_mic_tau(const double *mic_xyz, int M, int fs, const double *dirs /* [D][3] */, int D, double *mic_tau /* [M][D] */);
+void mcag_geom_pair_tau_from_mic_tau(const double *mic_tau, int M, int D, double *pair_tau /* [P][D] */);
+void mcag_geom_mel_bank(int N, int n_bands, int fs, float lo, float hi, double mic_dist, double *H /* [nb][N/2+1] */,
+                        double *fc_norm /* [nb] */, double *thresholds /* [nb] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

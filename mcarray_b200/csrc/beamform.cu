@@ -1,0 +1,104 @@
+// K4 ds_beamform: Beamformer::processFrame (Beamformer.cpp:51-71),
+//   Y[k] = (1/M) sum_c X_c[k] exp(j k phi_c),  phi_c = 2 pi fs/N/c * x_c * cos(DOA + pi/2).
+// The per-bin phase increment phi_c/(2 pi) arrives as 0.64 fixed-point turns (computed in double on the host from the
+// float-rounded grid angle the reference would use), so k*phi_c wraps exactly.
+//   k_ds_select : steer each frame to the S cells picked by selectDOA (BeamformingSeparationAndLocalisation.cpp:103-119)
+//   k_ds_fan    : steer every frame to all D directions (BASELINE config 3), CUDA-core tile version
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mcag {
+
+// steering table tab[d][c][k] = exp(j 2 pi k fx[d][c]) for the selected-cell beamformer (D*M*KP float2, L2 resident)
+__global__ void steer_table_kernel(const uint64_t *__restrict__ fx, int DM, int N, float2 *__restrict__ tab) {
+  const int KP = spec_pitch(N), K = N / 2 + 1;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)DM * KP) return;
+  const int k = (int)(i % KP);
+  tab[i] = (k < K) ? phase_ramp(fx[i / KP], k) : make_float2(0.f, 0.f);
+}
+int k_steer_table(const uint64_t *fx, int DM, int N, float2 *tab, cudaStream_t st) {
+  const long long n = (long long)DM * spec_pitch(N);
+  steer_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(fx, DM, N, tab);
+  MCAG_CHECK_LAUNCH();
+  return 0;
+}
+
+// one CTA per frame; out[b][t][s][k] for s < S, zeros for S <= s < C_out
+__global__ void __launch_bounds__(256) ds_select_kernel(const float2 *__restrict__ spec, int M, int N, const float2 *__restrict__ tab,
+                                                         const int32_t *__restrict__ cells, int S, int C_out, float2 *__restrict__ out) {
+  const int KP = spec_pitch(N), K = N / 2 + 1;
+  const long long bt = blockIdx.x;
+  const float2 *X = spec + bt * M * KP;
+  const float invM = 1.0f / (float)M;
+  for (int s = 0; s < C_out; ++s) {
+    float2 *o = out + (bt * C_out + s) * KP;
+    if (s >= S || s >= M) {
+      for (int k = threadIdx.x; k < KP; k += blockDim.x) o[k] = make_float2(0.f, 0.f);
+      continue;
+    }
+    const float2 *A = tab + (size_t)cells[bt * S + s] * M * KP;
+    for (int k = threadIdx.x; k < KP; k += blockDim.x) {
+      float2 acc = make_float2(0.f, 0.f);
+      if (k < K)
+        for (int c = 0; c < M; ++c) acc = cadd(acc, cmul(X[(size_t)c * KP + k], A[(size_t)c * KP + k]));   // channel order as :56-68
+      o[k] = make_float2(acc.x * invM, acc.y * invM);
+    }
+  }
+}
+
+int k_ds_select(const float2 *spec, int B, int T, int M, int N, const float2 *steer_tab, const int32_t *cells, int S, int C_out, float2 *out,
+                cudaStream_t st) {
+  const long long BT = (long long)B * T;
+  if (BT <= 0) return 0;
+  ds_select_kernel<<<(unsigned)BT, 256, 0, st>>>(spec, M, N, steer_tab, cells, S, C_out, out);
+  MCAG_CHECK_LAUNCH();
+  return 0;
+}
+
+// fan: CTA = (16-frame tile, 32-bin chunk, stream); the spectra tile is staged in shared memory, each thread owns one
+// (direction, bin) at a time and regenerates the M phasors once per 16 frames.
+constexpr int FAN_TF = 16, FAN_KC = 32;
+__global__ void __launch_bounds__(256) ds_fan_kernel(const float2 *__restrict__ spec, int T, int M, int N, const uint64_t *__restrict__ fx,
+                                                      int D, float2 *__restrict__ out) {
+  extern __shared__ float2 s_X[];   // [FAN_TF][M][FAN_KC]
+  const int KP = spec_pitch(N), K = N / 2 + 1;
+  const int t0 = blockIdx.x * FAN_TF, k0 = blockIdx.y * FAN_KC, b = blockIdx.z;
+  for (int i = threadIdx.x; i < FAN_TF * M * FAN_KC; i += blockDim.x) {
+    const int kk = i % FAN_KC, c = (i / FAN_KC) % M, f = i / (FAN_KC * M);
+    const int t = t0 + f, k = k0 + kk;
+    s_X[i] = (t < T && k < K) ? spec[(((long long)b * T + t) * M + c) * KP + k] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  const int kk = threadIdx.x % FAN_KC, k = k0 + kk;
+  const float invM = 1.0f / (float)M;
+  for (int d = threadIdx.x / FAN_KC; d < D; d += blockDim.x / FAN_KC) {
+    float2 acc[FAN_TF];
+#pragma unroll
+    for (int f = 0; f < FAN_TF; ++f) acc[f] = make_float2(0.f, 0.f);
+    for (int c = 0; c < M; ++c) {
+      const float2 a = phase_ramp(fx[(size_t)d * M + c], k);
+#pragma unroll
+      for (int f = 0; f < FAN_TF; ++f) acc[f] = cadd(acc[f], cmul(s_X[(f * M + c) * FAN_KC + kk], a));
+    }
+    if (k < KP) {
+#pragma unroll
+      for (int f = 0; f < FAN_TF; ++f)
+        if (t0 + f < T) out[(((long long)b * T + t0 + f) * D + d) * KP + k] = (k < K) ? make_float2(acc[f].x * invM, acc[f].y * invM) : make_float2(0.f, 0.f);
+    }
+  }
+}
+
+int k_ds_fan(const float2 *spec, int B, int T, int M, int N, const uint64_t *steer_fx, int D, float2 *out, cudaStream_t st) {
+  if (B <= 0 || T <= 0) return 0;
+  const int KP = spec_pitch(N);
+  size_t smem = sizeof(float2) * FAN_TF * M * FAN_KC;
+  if (smem > 200 * 1024) return mcag_set_error(1, "ds_fan: too many channels");
+  cudaFuncSetAttribute(ds_fan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid((T + FAN_TF - 1) / FAN_TF, (KP + FAN_KC - 1) / FAN_KC, B);
+  ds_fan_kernel<<<grid, 256, smem, st>>>(spec, T, M, N, steer_fx, D, out);
+  MCAG_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace mcag

@@ -1,0 +1,717 @@
+// C ABI (include/mcarray_b200.h): processor handles that chain the kernels of this directory, plus thin extern "C"
+// wrappers around the kernel launchers.  Host code only orchestrates: every arithmetic step of the hot path runs in a
+// CUDA kernel; there is no CPU fallback (a missing device or a failed launch is an error, never a silent detour).
+#include "../../include/mcarray_b200.h"
+#include "kernels.h"
+#include "common.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+thread_local std::string g_err;
+}
+int mcag_set_error(int code, const char *msg) { g_err = msg ? msg : ""; return code; }
+int mcag_set_cuda_error(cudaError_t e) { g_err = std::string("CUDA: ") + cudaGetErrorString(e); return MCAG_ERR_CUDA; }
+
+#define CU(call)                                              \
+  do {                                                        \
+    cudaError_t e__ = (call);                                 \
+    if (e__ != cudaSuccess) return mcag_set_cuda_error(e__);  \
+  } while (0)
+#define OK(call)                   \
+  do {                             \
+    int r__ = (call);              \
+    if (r__ != MCAG_OK) return r__; \
+  } while (0)
+
+namespace mcag {
+
+// turns (any real) -> unsigned 0.64 fixed point of frac(turns)
+static uint64_t turns_to_fx(double turns) {
+  double f = turns - std::floor(turns);          // [0, 1)
+  long double s = (long double)f * 18446744073709551616.0L;
+  if (s >= 18446744073709551615.0L) return 0;    // wrapped to a full turn
+  return (uint64_t)s;
+}
+
+// ---- small device helpers owned by the processors ----------------------------------------------------------------
+// power gate: SoundLocalisationImpl state machine (BeamformingSeparationAndLocalisation.cpp:55-101,
+// BinauralLocalisation.cpp:387-404,429-434).  One thread per stream, sequential over the frames of the call.
+struct GateState { double acc; double floor; int samples; int estimated; };
+
+__global__ void gate_kernel(const float *__restrict__ chan_pow, const float *__restrict__ chan_raw, int B, int T, int M, int N, int use_floor,
+                            int ccs_mode, float margin_db, int needed, GateState *__restrict__ gs, float *__restrict__ power_db,
+                            unsigned char *__restrict__ active) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  GateState s = gs[b];
+  const bool estimate = ccs_mode ? true : (use_floor != 0);   // FreqGCC estimates the floor even when it will not use it (:429)
+  for (int t = 0; t < T; ++t) {
+    const float *cp = chan_pow + ((long long)b * T + t) * M;
+    double lin = 0.0;
+    for (int m = 0; m < M; ++m) lin += (double)cp[m];
+    lin /= (double)M;
+    double power;
+    if (!s.estimated && estimate) {
+      if (ccs_mode) {
+        const float *cr = chan_raw + ((long long)b * T + t) * M;
+        double raw = 0.0;
+        for (int m = 0; m < M; ++m) raw += (double)cr[m] / (double)(N + 2);
+        s.acc += raw / (double)M * (double)N + 1e-10;
+      } else {
+        s.acc += lin * (double)N;
+      }
+      s.samples += N;
+      if (s.samples >= needed) {
+        s.estimated = 1;
+        s.acc /= (double)s.samples;
+        s.acc = 10.0 * log10(s.acc) + (double)margin_db;
+      }
+      s.floor = s.acc;
+      power = s.floor;
+    } else {
+      power = 10.0 * log10(lin);
+    }
+    power_db[(long long)b * T + t] = (float)power;
+    active[(long long)b * T + t] = (power > s.floor || !use_floor) ? 1 : 0;
+  }
+  gs[b] = s;
+}
+
+// hold the last active selection on gated-off frames (_currentDOA / _prob persist, BSAL.cpp:87-95)
+__global__ void carry_cells_kernel(const int32_t *__restrict__ raw_idx, const float *__restrict__ raw_prob, const unsigned char *__restrict__ active,
+                                   int B, int T, int S, int32_t *__restrict__ cell_state, float *__restrict__ prob_state,
+                                   int32_t *__restrict__ cells, float *__restrict__ prob) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * S) return;
+  const int b = i / S, s = i - b * S;
+  int32_t c = cell_state[i];
+  float p = prob_state[i];
+  for (int t = 0; t < T; ++t) {
+    const long long o = ((long long)b * T + t) * S + s;
+    if (active[(long long)b * T + t]) { c = raw_idx[o]; p = raw_prob[o]; }
+    cells[o] = c; prob[o] = p;
+  }
+  cell_state[i] = c; prob_state[i] = p;
+}
+
+__global__ void s16_to_f32_kernel(const int16_t *__restrict__ in, float *__restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+__global__ void f64_to_f32_kernel(const double *__restrict__ in, float *__restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+
+int k_frame_power_raw(const float2 *spec, long long rows, int N, float *raw, cudaStream_t st);   // below
+
+__global__ void frame_raw_kernel(const float2 *__restrict__ spec, long long rows, int N, float *__restrict__ raw) {
+  const int KP = spec_pitch(N), K = N / 2 + 1;
+  const long long row = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float2 *s = spec + row * KP;
+  float acc = 0.f;
+  for (int k = threadIdx.x & 31; k < K; k += 32) { float2 v = s[k]; acc += v.x * v.x + v.y * v.y; }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) raw[row] = acc;
+}
+int k_frame_power_raw(const float2 *spec, long long rows, int N, float *raw, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  frame_raw_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(spec, rows, N, raw);
+  MCAG_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace mcag
+
+using namespace mcag;
+
+// ======================================================================================================================
+struct DevBuf {
+  void *p = nullptr; size_t bytes = 0;
+  int alloc(size_t n) {
+    release();
+    if (n == 0) n = 16;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) { p = nullptr; mcag_set_cuda_error(e); return MCAG_ERR_NOMEM; }
+    bytes = n;
+    return MCAG_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct mcag_proc_s {
+  mcag_config cfg;
+  int B, M, N, hop, K, KP, P, D, S, Cs /* synthesised channels */, Cout /* channels the caller sees */, Tmax, L;
+  int rows;
+  cudaStream_t stream = nullptr;
+  long long launches = 0, frames_total = 0;
+  int frames_last = 0;
+  // input FIFO (ping-pong), per row capacity fifo_cap floats, fill = carried samples (same for every row)
+  DevBuf fifo[2]; int fifo_cur = 0; long long fifo_cap = 0; int fill = 0;
+  DevBuf stage_in, stage_out;   // device staging for non-f32 input / output conversion
+  DevBuf win, tw, spec, chan_pow, chan_raw, power_db, active, gate;
+  DevBuf pair_fx, corr, esum, energy, energy_state, raw_idx, raw_prob, cells, prob, cell_state, prob_state;
+  DevBuf steer_fx, steer_tab, beams, tail[2], out_dev; int tail_cur = 0;
+  DevBuf lags, curves, curve_state, started;
+  DevBuf mic_fx;
+  DevBuf H, H2, thr, stats, gains, Q, noise, dec, qtrace;
+  void *pin_in = nullptr, *pin_out = nullptr; size_t pin_in_bytes = 0, pin_out_bytes = 0;
+  std::vector<double> h_window;
+};
+
+static int upload(DevBuf &b, const void *src, size_t bytes, cudaStream_t st) {
+  OK(b.alloc(bytes));
+  CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st));
+  return MCAG_OK;
+}
+static int upload_fx(DevBuf &b, const double *turns, size_t n, cudaStream_t st) {
+  std::vector<uint64_t> fx(n);
+  for (size_t i = 0; i < n; ++i) fx[i] = turns_to_fx(turns[i]);
+  OK(upload(b, fx.data(), n * sizeof(uint64_t), st));
+  CU(cudaStreamSynchronize(st));
+  return MCAG_OK;
+}
+
+static int init_state(mcag_proc p) {
+  cudaStream_t st = p->stream;
+  p->fill = 0; p->fifo_cur = 0; p->tail_cur = 0; p->frames_total = 0; p->frames_last = 0;
+  if (p->gate.p) {
+    std::vector<GateState> gs((size_t)p->B);
+    for (auto &g : gs) { g.acc = 0; g.floor = 0; g.samples = 0; g.estimated = p->cfg.noise_preestimated ? 1 : 0; }
+    CU(cudaMemcpyAsync(p->gate.p, gs.data(), gs.size() * sizeof(GateState), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  if (p->energy_state.p) CU(cudaMemsetAsync(p->energy_state.p, 0, p->energy_state.bytes, st));
+  if (p->curve_state.p) CU(cudaMemsetAsync(p->curve_state.p, 0, p->curve_state.bytes, st));
+  if (p->started.p) CU(cudaMemsetAsync(p->started.p, 0, p->started.bytes, st));
+  if (p->cell_state.p) {
+    std::vector<int32_t> c((size_t)p->B * p->S, p->D);     // row D of the steering table = the initial DOA of 0 rad (BSAL.cpp:51)
+    std::vector<float> pr((size_t)p->B * p->S, -1.0f);     // wipp::set(-1.0, _prob) (BSAL.cpp:52)
+    CU(cudaMemcpyAsync(p->cell_state.p, c.data(), c.size() * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(p->prob_state.p, pr.data(), pr.size() * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  for (int i = 0; i < 2; ++i) if (p->tail[i].p) CU(cudaMemsetAsync(p->tail[i].p, 0, p->tail[i].bytes, st));
+  if (p->Q.p) { CU(cudaMemsetAsync(p->Q.p, 0, p->Q.bytes, st)); CU(cudaMemsetAsync(p->noise.p, 0, p->noise.bytes, st)); }
+  CU(cudaStreamSynchronize(st));
+  return MCAG_OK;
+}
+
+extern "C" {
+
+const char *mcag_last_error(void) { return g_err.c_str(); }
+int mcag_version(void) { return 100; }
+
+void mcag_config_init(mcag_config *c) {
+  std::memset(c, 0, sizeof(*c));
+  c->frame_size = 512; c->hop = 256; c->n_channels = 2; c->n_streams = 1; c->max_frames_per_call = 256;
+  c->n_sources = 1; c->energy_memory = 0.8f; c->corr_memory = 0.8f; c->noise_margin_db = 3.0f; c->floor_seconds = 3.0f;
+  c->mask_method = 1; c->n_bands = 45;
+}
+
+int mcag_create(const mcag_config *cfg, mcag_proc *out) {
+  if (!cfg || !out) return mcag_set_error(MCAG_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return mcag_set_error(MCAG_ERR_CUDA, "no CUDA device: mcarray_b200 has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return mcag_set_error(MCAG_ERR_INVALID, "bad device ordinal");
+  const int N = cfg->frame_size;
+  if (N != 256 && N != 512 && N != 1024 && N != 2048) return mcag_set_error(MCAG_ERR_INVALID, "frame_size must be 256, 512, 1024 or 2048");
+  if (cfg->hop <= 0 || (N % cfg->hop) || (cfg->hop & 3) || N / cfg->hop > 4) return mcag_set_error(MCAG_ERR_INVALID, "hop must divide N (N/hop <= 4) and be a multiple of 4");
+  if (cfg->n_channels < 1 || cfg->n_streams < 1 || cfg->max_frames_per_call < 1) return mcag_set_error(MCAG_ERR_INVALID, "bad channel / stream / frame counts");
+  const int kind = cfg->kind;
+  if ((kind == MCAG_KIND_MASK || kind == MCAG_KIND_FREQGCC) && cfg->n_channels != 2)
+    return mcag_set_error(MCAG_ERR_INVALID, "Binaural masking is only working for 2 channels.");   // FastBinauralMasking.cpp:88-91
+  CU(cudaSetDevice(cfg->device));
+
+  mcag_proc p = new mcag_proc_s();
+  p->cfg = *cfg;
+  p->B = cfg->n_streams; p->M = cfg->n_channels; p->N = N; p->hop = cfg->hop; p->K = N / 2 + 1; p->KP = spec_pitch(N);
+  p->P = p->M * (p->M - 1) / 2; p->D = cfg->n_dirs; p->S = cfg->n_sources > 0 ? cfg->n_sources : 1; p->Tmax = cfg->max_frames_per_call;
+  p->L = 2 * cfg->max_lag + 1; p->rows = p->B * p->M;
+  p->Cs = 0; p->Cout = 0;
+  if (kind == MCAG_KIND_SSL) { p->Cs = p->S < p->M ? p->S : p->M; p->Cout = p->M; }
+  if (kind == MCAG_KIND_MASK) { p->Cs = 2; p->Cout = 2; }
+  int rc = MCAG_OK;
+  auto fail = [&](int code) { mcag_destroy(p); return code; };
+  if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(mcag_set_error(MCAG_ERR_CUDA, "stream creation failed"));
+  cudaStream_t st = p->stream;
+  const size_t B = p->B, M = p->M, T = p->Tmax, KP = p->KP, D = p->D, P = p->P, S = p->S;
+
+  // window + twiddles
+  p->h_window.resize(N);
+  for (int n = 0; n < N; ++n) p->h_window[n] = cfg->window ? cfg->window[n] : std::sqrt(0.5 * (1.0 - std::cos(2.0 * M_PI * n / N)));
+  { std::vector<float> w(N); for (int n = 0; n < N; ++n) w[n] = (float)p->h_window[n];
+    if ((rc = upload(p->win, w.data(), N * sizeof(float), st))) return fail(rc); CU(cudaStreamSynchronize(st)); }
+  if ((rc = p->tw.alloc(sizeof(float2) * N / 2))) return fail(rc);
+  if ((rc = mcag_k_twiddles(N, p->tw.p, st))) return fail(rc);
+
+  // FIFO: carried samples (< N) + one call's worth of new samples; a call completing Tmax frames consumes Tmax*hop
+  p->fifo_cap = ((long long)N + (long long)(T + 1) * p->hop + 3) & ~3LL;
+  for (int i = 0; i < 2; ++i) if ((rc = p->fifo[i].alloc(sizeof(float) * p->rows * p->fifo_cap))) return fail(rc);
+  if ((rc = p->spec.alloc(sizeof(float2) * B * T * M * KP))) return fail(rc);
+  if ((rc = p->chan_pow.alloc(sizeof(float) * B * T * M))) return fail(rc);
+  if ((rc = p->power_db.alloc(sizeof(float) * B * T))) return fail(rc);
+  if ((rc = p->active.alloc(B * T))) return fail(rc);
+  if ((rc = p->gate.alloc(sizeof(GateState) * B))) return fail(rc);
+  if (cfg->floor_ccs_power) if ((rc = p->chan_raw.alloc(sizeof(float) * B * T * M))) return fail(rc);
+
+  const bool loc = kind == MCAG_KIND_SSL || kind == MCAG_KIND_SL;
+  if (loc || kind == MCAG_KIND_FREQGCC) {
+    if (D < 3 || !cfg->pair_tau) return fail(mcag_set_error(MCAG_ERR_INVALID, "pair_tau [P][D] with D >= 3 required"));
+    std::vector<double> turns(P * D);
+    for (size_t i = 0; i < P * D; ++i) turns[i] = cfg->pair_tau[i] / (double)N;   // exp(+j 2 pi k tau / N)
+    if ((rc = upload_fx(p->pair_fx, turns.data(), turns.size(), st))) return fail(rc);
+    if ((rc = p->corr.alloc(sizeof(float) * B * T * P * D))) return fail(rc);
+  }
+  if (loc || kind == MCAG_KIND_SRP) {
+    if ((rc = p->esum.alloc(sizeof(float) * B * T * D))) return fail(rc);
+    if ((rc = p->energy.alloc(sizeof(float) * B * T * D))) return fail(rc);
+    if ((rc = p->energy_state.alloc(sizeof(float) * B * D))) return fail(rc);
+    if ((rc = p->raw_idx.alloc(4 * B * T * S)) || (rc = p->raw_prob.alloc(4 * B * T * S)) || (rc = p->cells.alloc(4 * B * T * S)) ||
+        (rc = p->prob.alloc(4 * B * T * S)) || (rc = p->cell_state.alloc(4 * B * S)) || (rc = p->prob_state.alloc(4 * B * S)))
+      return fail(rc);
+  }
+  if (kind == MCAG_KIND_SSL) {
+    if (!cfg->steer_turns) return fail(mcag_set_error(MCAG_ERR_INVALID, "steer_turns [D+1][M] required (row D = initial DOA)"));
+    if ((rc = upload_fx(p->steer_fx, cfg->steer_turns, (D + 1) * M, st))) return fail(rc);
+    if ((rc = p->steer_tab.alloc(sizeof(float2) * (D + 1) * M * KP))) return fail(rc);
+    if ((rc = k_steer_table(p->steer_fx.as<uint64_t>(), (int)((D + 1) * M), N, p->steer_tab.as<float2>(), st))) return fail(rc);
+  }
+  if (kind == MCAG_KIND_FREQGCC) {
+    if ((rc = p->curves.alloc(sizeof(float) * B * T * D)) || (rc = p->curve_state.alloc(sizeof(float) * B * D)) || (rc = p->started.alloc(B)) ||
+        (rc = p->cells.alloc(4 * B * T)))
+      return fail(rc);
+  }
+  if (kind == MCAG_KIND_TDOA) {
+    if (p->M < 2) return fail(mcag_set_error(MCAG_ERR_INVALID, "TDOA needs at least 2 channels"));
+    if ((rc = p->lags.alloc(4 * B * T * P))) return fail(rc);
+    if (cfg->emit & MCAG_EMIT_CURVES) if ((rc = p->curves.alloc(sizeof(float) * B * T * P * p->L))) return fail(rc);
+  }
+  if (kind == MCAG_KIND_DSFAN) {
+    if (D < 1 || !cfg->steer_turns) return fail(mcag_set_error(MCAG_ERR_INVALID, "steer_turns [D][M] required"));
+    if ((rc = upload_fx(p->steer_fx, cfg->steer_turns, D * M, st))) return fail(rc);
+    if ((rc = p->beams.alloc(sizeof(float2) * B * T * D * KP))) return fail(rc);
+  }
+  if (kind == MCAG_KIND_SRP) {
+    if (D < 3 || !cfg->mic_tau) return fail(mcag_set_error(MCAG_ERR_INVALID, "mic_tau [M][D] with D >= 3 required"));
+    std::vector<double> turns(D * M);   // device layout [D][M], exp(-j 2 pi k tau_m / N)
+    for (size_t m = 0; m < M; ++m) for (size_t d = 0; d < D; ++d) turns[d * M + m] = -cfg->mic_tau[m * D + d] / (double)N;
+    if ((rc = upload_fx(p->mic_fx, turns.data(), turns.size(), st))) return fail(rc);
+  }
+  if (p->Cs > 0) {
+    if ((rc = p->beams.alloc(sizeof(float2) * B * T * (kind == MCAG_KIND_MASK ? 2 : p->Cs) * KP))) return fail(rc);
+    for (int i = 0; i < 2; ++i) if ((rc = p->tail[i].alloc(sizeof(float) * B * p->Cs * (N - p->hop)))) return fail(rc);
+    if ((rc = p->out_dev.alloc(sizeof(float) * B * p->Cs * T * p->hop))) return fail(rc);
+  }
+  if (kind == MCAG_KIND_MASK) {
+    const size_t nb = cfg->n_bands;
+    if (nb < 1 || !cfg->band_coefs || !cfg->band_thresholds) return fail(mcag_set_error(MCAG_ERR_INVALID, "band_coefs / band_thresholds required"));
+    std::vector<float> H(nb * KP, 0.f), H2(nb * KP, 0.f), thr(nb);
+    for (size_t b = 0; b < nb; ++b) {
+      for (int k = 0; k < p->K; ++k) { double h = cfg->band_coefs[b * p->K + k]; H[b * KP + k] = (float)h; H2[b * KP + k] = (float)(h * h); }
+      thr[b] = (float)cfg->band_thresholds[b];
+    }
+    if ((rc = upload(p->H, H.data(), H.size() * 4, st)) || (rc = upload(p->H2, H2.data(), H2.size() * 4, st)) || (rc = upload(p->thr, thr.data(), nb * 4, st)))
+      return fail(rc);
+    CU(cudaStreamSynchronize(st));
+    if ((rc = p->stats.alloc(4 * B * T * nb * 6)) || (rc = p->gains.alloc(4 * B * T * nb * 2)) || (rc = p->Q.alloc(4 * B * nb)) ||
+        (rc = p->noise.alloc(4 * B * nb)) || (rc = p->dec.alloc(B * T * nb)) || (rc = p->qtrace.alloc(4 * B * T * nb)))
+      return fail(rc);
+  }
+  if ((rc = init_state(p))) return fail(rc);
+  *out = p;
+  return MCAG_OK;
+}
+
+void mcag_destroy(mcag_proc p) {
+  if (!p) return;
+  cudaSetDevice(p->cfg.device);
+  if (p->stream) cudaStreamSynchronize(p->stream);
+  DevBuf *all[] = {&p->fifo[0], &p->fifo[1], &p->stage_in, &p->stage_out, &p->win, &p->tw, &p->spec, &p->chan_pow, &p->chan_raw, &p->power_db,
+                   &p->active, &p->gate, &p->pair_fx, &p->corr, &p->esum, &p->energy, &p->energy_state, &p->raw_idx, &p->raw_prob, &p->cells,
+                   &p->prob, &p->cell_state, &p->prob_state, &p->steer_fx, &p->steer_tab, &p->beams, &p->tail[0], &p->tail[1], &p->out_dev,
+                   &p->lags, &p->curves, &p->curve_state, &p->started, &p->mic_fx, &p->H, &p->H2, &p->thr, &p->stats, &p->gains, &p->Q,
+                   &p->noise, &p->dec, &p->qtrace};
+  for (DevBuf *b : all) b->release();
+  if (p->pin_in) cudaFreeHost(p->pin_in);
+  if (p->pin_out) cudaFreeHost(p->pin_out);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+}
+
+int mcag_reset(mcag_proc p) {
+  if (!p) return mcag_set_error(MCAG_ERR_INVALID, "null handle");
+  CU(cudaSetDevice(p->cfg.device));
+  return init_state(p);
+}
+
+int mcag_flush_input(mcag_proc p) {
+  if (!p) return mcag_set_error(MCAG_ERR_INVALID, "null handle");
+  p->fill = 0;
+  return MCAG_OK;
+}
+
+int mcag_get_info(mcag_proc p, mcag_info *i) {
+  if (!p || !i) return mcag_set_error(MCAG_ERR_INVALID, "null argument");
+  i->frame_size = p->hop; i->window_size = p->N; i->hop = p->hop; i->analysis_length = p->N + 2; i->one_sided_length = p->K;
+  i->n_channels = p->M; i->n_streams = p->B; i->max_latency = p->N; i->n_dirs = p->D; i->n_pairs = p->P; i->n_sources = p->S;
+  i->n_out_channels = p->Cout; i->spectrum_pitch = p->KP; i->max_frames_per_call = p->Tmax;
+  return MCAG_OK;
+}
+
+int mcag_synchronize(mcag_proc p) {
+  if (!p) return mcag_set_error(MCAG_ERR_INVALID, "null handle");
+  CU(cudaStreamSynchronize(p->stream));
+  return MCAG_OK;
+}
+int mcag_frames_done(mcag_proc p) { return p ? p->frames_last : 0; }
+long long mcag_frames_total(mcag_proc p) { return p ? p->frames_total : 0; }
+void *mcag_stream(mcag_proc p) { return p ? (void *)p->stream : nullptr; }
+long long mcag_kernel_launches(mcag_proc p) { return p ? p->launches : 0; }
+
+void *mcag_host_alloc(long long bytes) {
+  void *ptr = nullptr;
+  if (cudaMallocHost(&ptr, (size_t)bytes) != cudaSuccess) { mcag_set_error(MCAG_ERR_NOMEM, "cudaMallocHost failed"); return nullptr; }
+  return ptr;
+}
+void mcag_host_free(void *ptr) { if (ptr) cudaFreeHost(ptr); }
+
+}  // extern "C"
+
+// ----------------------------------------------------------------------------------------------------------------------
+// the frame pipeline: T complete frames are available at `x` (device, rows x pitch); results land in the handle's arrays,
+// synthesised audio (if any) in out_dev [B*Cs][T*hop]
+// ----------------------------------------------------------------------------------------------------------------------
+static int run_frames(mcag_proc p, const float *x, long long pitch, int T) {
+  cudaStream_t st = p->stream;
+  const int B = p->B, M = p->M, N = p->N, hop = p->hop, D = p->D, P = p->P, S = p->S, kind = p->cfg.kind;
+  const long long BT = (long long)B * T;
+  float2 *spec = p->spec.as<float2>();
+  OK(k_stft(x, pitch, p->rows, M, T, N, hop, p->win.as<float>(), p->tw.as<float2>(), spec, p->chan_pow.as<float>(), st));
+  p->launches += (N == 256) ? 2 : 1;
+  if (p->cfg.floor_ccs_power) { OK(k_frame_power_raw(spec, BT * M, N, p->chan_raw.as<float>(), st)); p->launches++; }
+  const int needed = (int)(p->cfg.floor_seconds * (float)p->cfg.sample_rate);
+  gate_kernel<<<(B + 127) / 128, 128, 0, st>>>(p->chan_pow.as<float>(), p->chan_raw.as<float>(), B, T, M, N, p->cfg.use_power_floor,
+                                               p->cfg.floor_ccs_power, p->cfg.noise_margin_db, needed, p->gate.as<GateState>(),
+                                               p->power_db.as<float>(), p->active.as<unsigned char>());
+  MCAG_CHECK_LAUNCH();
+  p->launches++;
+  const unsigned char *active = p->active.as<unsigned char>();
+
+  if (kind == MCAG_KIND_SSL || kind == MCAG_KIND_SL) {
+    OK(k_gcc_tau(spec, B, T, M, N, p->pair_fx.as<uint64_t>(), D, p->corr.as<float>(), st));
+    p->launches += (D <= 40) ? 1 : (D + 63) / 64;
+    const float a = p->cfg.energy_memory, b = 1.0f - p->cfg.energy_memory;   // float arithmetic as SteeringBeamforming.cpp:134,139
+    OK(k_pair_sum(p->corr.as<float>(), BT, P, D, b, p->esum.as<float>(), st));
+    OK(k_energy_scan(p->esum.as<float>(), B, T, D, a, active, p->energy_state.as<float>(), p->energy.as<float>(), st));
+    OK(k_select_doa(p->energy.as<float>(), BT, D, P, S, p->raw_idx.as<int32_t>(), p->raw_prob.as<float>(), st));
+    carry_cells_kernel<<<(B * S + 127) / 128, 128, 0, st>>>(p->raw_idx.as<int32_t>(), p->raw_prob.as<float>(), active, B, T, S,
+                                                            p->cell_state.as<int32_t>(), p->prob_state.as<float>(), p->cells.as<int32_t>(),
+                                                            p->prob.as<float>());
+    MCAG_CHECK_LAUNCH();
+    p->launches += 4;
+    if (kind == MCAG_KIND_SSL) {
+      OK(k_ds_select(spec, B, T, M, N, p->steer_tab.as<float2>(), p->cells.as<int32_t>(), S, p->Cs, p->beams.as<float2>(), st));
+      OK(k_istft(p->beams.as<float2>(), B, T, p->Cs, p->Cs, N, hop, p->win.as<float>(), p->tw.as<float2>(), p->tail[p->tail_cur].as<float>(),
+                 p->tail[p->tail_cur ^ 1].as<float>(), p->out_dev.as<float>(), (long long)T * hop, st));
+      p->tail_cur ^= 1;
+      p->launches += 2;
+    }
+  } else if (kind == MCAG_KIND_FREQGCC) {
+    OK(k_gcc_tau(spec, B, T, 2, N, p->pair_fx.as<uint64_t>(), D, p->corr.as<float>(), st));
+    OK(k_curve_scan_argmax(p->corr.as<float>(), B, T, D, 1.0f, p->cfg.corr_memory, active, p->curve_state.as<float>(),
+                           p->started.as<unsigned char>(), p->curves.as<float>(), p->cells.as<int32_t>(), st));
+    p->launches += ((D <= 40) ? 1 : (D + 63) / 64) + 3;
+  } else if (kind == MCAG_KIND_TDOA) {
+    OK(k_tdoa_lags(spec, B, T, M, N, p->cfg.max_lag, p->tw.as<float2>(), p->curves.p ? p->curves.as<float>() : nullptr, p->lags.as<int32_t>(),
+                   nullptr, st));
+    p->launches++;
+  } else if (kind == MCAG_KIND_DSFAN) {
+    OK(k_ds_fan(spec, B, T, M, N, p->steer_fx.as<uint64_t>(), D, p->beams.as<float2>(), st));
+    p->launches++;
+  } else if (kind == MCAG_KIND_SRP) {
+    OK(mcag_k_srp_tensor(spec, B, T, M, N, p->mic_fx.as<uint64_t>(), D, p->esum.as<float>(), st));
+    // the pair sum enters the smoothing scaled by (1 - a), like every pair correlation (SteeringBeamforming.cpp:139)
+    OK(k_pair_sum(p->esum.as<float>(), BT, 1, D, 1.0f - p->cfg.energy_memory, p->energy.as<float>(), st));
+    OK(k_energy_scan(p->energy.as<float>(), B, T, D, p->cfg.energy_memory, active, p->energy_state.as<float>(), p->energy.as<float>(), st));
+    OK(k_select_doa(p->energy.as<float>(), BT, D, P, S, p->raw_idx.as<int32_t>(), p->raw_prob.as<float>(), st));
+    carry_cells_kernel<<<(B * S + 127) / 128, 128, 0, st>>>(p->raw_idx.as<int32_t>(), p->raw_prob.as<float>(), active, B, T, S,
+                                                            p->cell_state.as<int32_t>(), p->prob_state.as<float>(), p->cells.as<int32_t>(),
+                                                            p->prob.as<float>());
+    MCAG_CHECK_LAUNCH();
+    p->launches += 5;
+  } else if (kind == MCAG_KIND_MASK) {
+    const int nb = p->cfg.n_bands;
+    if (p->cfg.mask_method != 5) {   // NOTHING: pass-through (FastBinauralMasking.cpp:130-134)
+      OK(k_mask_stats(spec, BT, N, p->H2.as<float>(), nb, p->stats.as<float>(), st));
+      OK(k_mask_scan(p->stats.as<float>(), B, T, N, nb, p->cfg.mask_method, p->cfg.mask_alg, p->thr.as<float>(), p->Q.as<float>(),
+                     p->noise.as<float>(), (int)(p->frames_total > 2 ? 2 : p->frames_total), p->gains.as<float>(), p->dec.as<unsigned char>(),
+                     p->qtrace.as<float>(), st));
+      OK(k_mask_apply(spec, BT, N, p->H.as<float>(), nb, p->gains.as<float>(), st));
+      p->launches += 3;
+    }
+    OK(k_istft(spec, B, T, 2, 2, N, hop, p->win.as<float>(), p->tw.as<float2>(), p->tail[p->tail_cur].as<float>(),
+               p->tail[p->tail_cur ^ 1].as<float>(), p->out_dev.as<float>(), (long long)T * hop, st));
+    p->tail_cur ^= 1;
+    p->launches++;
+  }
+  return MCAG_OK;
+}
+
+// frames completed by appending nsamples to a FIFO that already holds `fill`
+static int frames_for(const mcag_proc p, int nsamples) {
+  const long long have = (long long)p->fill + nsamples;
+  return have < p->N ? 0 : (int)((have - p->N) / p->hop + 1);
+}
+
+// core: new samples are on the device at d_new (rows x pitch).  Handles the FIFO, runs the frames, leaves audio in out_dev.
+static int process_device_core(mcag_proc p, const float *d_new, long long pitch, int nsamples, int *T_out) {
+  cudaStream_t st = p->stream;
+  const int T = frames_for(p, nsamples);
+  if (T > p->Tmax) return mcag_set_error(MCAG_ERR_CAPACITY, "process: more frames than max_frames_per_call");
+  if ((long long)p->fill + nsamples > p->fifo_cap) return mcag_set_error(MCAG_ERR_CAPACITY, "process: chunk larger than the input FIFO");
+  const float *x; long long xp;
+  float *cur = p->fifo[p->fifo_cur].as<float>(), *nxt = p->fifo[p->fifo_cur ^ 1].as<float>();
+  if (p->fill == 0 && (pitch % 4) == 0 && ((uintptr_t)d_new % 16) == 0) {
+    x = d_new; xp = pitch;                       // run straight from the caller's buffer
+  } else {
+    CU(cudaMemcpy2DAsync(cur + p->fill, p->fifo_cap * 4, d_new, pitch * 4, (size_t)nsamples * 4, p->rows, cudaMemcpyDeviceToDevice, st));
+    x = cur; xp = p->fifo_cap;
+  }
+  if (T > 0) OK(run_frames(p, x, xp, T));
+  // carry the unconsumed samples
+  const long long have = (long long)p->fill + nsamples, consumed = (long long)T * p->hop, left = have - consumed;
+  if (left > 0) {
+    if (x == d_new) {
+      CU(cudaMemcpy2DAsync(cur, p->fifo_cap * 4, d_new + consumed, pitch * 4, (size_t)left * 4, p->rows, cudaMemcpyDeviceToDevice, st));
+    } else if (consumed > 0) {
+      CU(cudaMemcpy2DAsync(nxt, p->fifo_cap * 4, cur + consumed, p->fifo_cap * 4, (size_t)left * 4, p->rows, cudaMemcpyDeviceToDevice, st));
+      p->fifo_cur ^= 1;
+    }
+  }
+  p->fill = (int)left;
+  p->frames_last = T;
+  p->frames_total += T;
+  *T_out = T;
+  return MCAG_OK;
+}
+
+template <class Tin> struct Conv;
+template <> struct Conv<float> { static constexpr int id = 0; };
+template <> struct Conv<double> { static constexpr int id = 1; };
+template <> struct Conv<int16_t> { static constexpr int id = 2; };
+
+static int ensure_pinned(void **ptr, size_t *have, size_t need) {
+  if (*have >= need) return MCAG_OK;
+  if (*ptr) cudaFreeHost(*ptr);
+  *ptr = nullptr; *have = 0;
+  CU(cudaMallocHost(ptr, need));
+  *have = need;
+  return MCAG_OK;
+}
+
+template <class Tio>
+static int process_host(mcag_proc p, const Tio *const *in, const Tio *in_packed, long long in_pitch, int nsamples, Tio *const *out, Tio *out_packed,
+                        long long out_pitch, int out_capacity, int *nsamples_out) {
+  if (!p) return mcag_set_error(MCAG_ERR_INVALID, "null handle");
+  if (nsamples < 0 || (!in && !in_packed && nsamples > 0)) return mcag_set_error(MCAG_ERR_INVALID, "bad input");
+  CU(cudaSetDevice(p->cfg.device));
+  cudaStream_t st = p->stream;
+  const int rows = p->rows;
+  const int T = frames_for(p, nsamples);
+  if (T > p->Tmax) return mcag_set_error(MCAG_ERR_CAPACITY, "process: more frames than max_frames_per_call");
+  if ((long long)p->fill + nsamples > p->fifo_cap) return mcag_set_error(MCAG_ERR_CAPACITY, "process: chunk larger than the input FIFO");
+  const bool want_audio = p->Cs > 0 && (out || out_packed);
+  if (want_audio && (long long)T * p->hop > out_capacity) return mcag_set_error(MCAG_ERR_CAPACITY, "process: output buffer too small");
+
+  // ---- host -> device: append to the FIFO (f32 directly; f64 / s16 through a device staging buffer + convert kernel)
+  float *cur = p->fifo[p->fifo_cur].as<float>();
+  if (nsamples > 0) {
+    if (Conv<Tio>::id == 0) {
+      if (in_packed) {
+        CU(cudaMemcpy2DAsync(cur + p->fill, p->fifo_cap * 4, in_packed, in_pitch * 4, (size_t)nsamples * 4, rows, cudaMemcpyHostToDevice, st));
+      } else {
+        for (int r = 0; r < rows; ++r) CU(cudaMemcpyAsync(cur + (long long)r * p->fifo_cap + p->fill, in[r], (size_t)nsamples * 4, cudaMemcpyHostToDevice, st));
+      }
+    } else {
+      const size_t need = (size_t)rows * nsamples * sizeof(Tio);
+      if (p->stage_in.bytes < need) OK(p->stage_in.alloc(need));
+      if (p->stage_out.bytes < (size_t)rows * nsamples * 4) OK(p->stage_out.alloc((size_t)rows * nsamples * 4));
+      if (in_packed) CU(cudaMemcpy2DAsync(p->stage_in.p, (size_t)nsamples * sizeof(Tio), in_packed, in_pitch * sizeof(Tio), (size_t)nsamples * sizeof(Tio), rows, cudaMemcpyHostToDevice, st));
+      else for (int r = 0; r < rows; ++r) CU(cudaMemcpyAsync((char *)p->stage_in.p + (size_t)r * nsamples * sizeof(Tio), in[r], (size_t)nsamples * sizeof(Tio), cudaMemcpyHostToDevice, st));
+      const long long n = (long long)rows * nsamples;
+      if (Conv<Tio>::id == 1) f64_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p->stage_in.as<double>(), p->stage_out.as<float>(), n);
+      else s16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p->stage_in.as<int16_t>(), p->stage_out.as<float>(), n);
+      MCAG_CHECK_LAUNCH();
+      p->launches++;
+      CU(cudaMemcpy2DAsync(cur + p->fill, p->fifo_cap * 4, p->stage_out.p, (size_t)nsamples * 4, (size_t)nsamples * 4, rows, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  if (T > 0) OK(run_frames(p, cur, p->fifo_cap, T));
+  const long long have = (long long)p->fill + nsamples, consumed = (long long)T * p->hop, left = have - consumed;
+  if (left > 0 && consumed > 0) {
+    float *nxt = p->fifo[p->fifo_cur ^ 1].as<float>();
+    CU(cudaMemcpy2DAsync(nxt, p->fifo_cap * 4, cur + consumed, p->fifo_cap * 4, (size_t)left * 4, rows, cudaMemcpyDeviceToDevice, st));
+    p->fifo_cur ^= 1;
+  }
+  p->fill = (int)left;
+  p->frames_last = T;
+  p->frames_total += T;
+
+  // ---- device -> host: synthesised audio; channels >= Cs are zeros (BeamformingSeparationAndLocalisation.cpp:117-118)
+  const int nout = T * p->hop;
+  if (want_audio && nout > 0) {
+    const int orow = p->B * p->Cs;
+    OK(ensure_pinned(&p->pin_out, &p->pin_out_bytes, (size_t)orow * nout * 4));
+    CU(cudaMemcpyAsync(p->pin_out, p->out_dev.p, (size_t)orow * nout * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const float *src = (const float *)p->pin_out;
+    for (int b = 0; b < p->B; ++b)
+      for (int c = 0; c < p->Cout; ++c) {
+        Tio *dst = out_packed ? out_packed + ((long long)b * p->Cout + c) * out_pitch : out[(long long)b * p->Cout + c];
+        if (!dst) continue;
+        if (c < p->Cs) {
+          const float *s = src + ((long long)b * p->Cs + c) * nout;
+          if (Conv<Tio>::id == 2) for (int i = 0; i < nout; ++i) { float v = nearbyintf(s[i]); dst[i] = (Tio)(v > 32767.f ? 32767.f : (v < -32768.f ? -32768.f : v)); }
+          else for (int i = 0; i < nout; ++i) dst[i] = (Tio)s[i];
+        } else {
+          for (int i = 0; i < nout; ++i) dst[i] = (Tio)0;
+        }
+      }
+  } else {
+    CU(cudaStreamSynchronize(st));
+  }
+  if (nsamples_out) *nsamples_out = p->Cs > 0 ? nout : 0;
+  return MCAG_OK;
+}
+
+extern "C" {
+
+int mcag_process_f32(mcag_proc p, const float *const *in, int nsamples, float *const *out, int out_capacity, int *nsamples_out) {
+  return process_host<float>(p, in, nullptr, 0, nsamples, out, nullptr, 0, out_capacity, nsamples_out);
+}
+int mcag_process_f64(mcag_proc p, const double *const *in, int nsamples, double *const *out, int out_capacity, int *nsamples_out) {
+  return process_host<double>(p, in, nullptr, 0, nsamples, out, nullptr, 0, out_capacity, nsamples_out);
+}
+int mcag_process_s16(mcag_proc p, const int16_t *const *in, int nsamples, int16_t *const *out, int out_capacity, int *nsamples_out) {
+  return process_host<int16_t>(p, in, nullptr, 0, nsamples, out, nullptr, 0, out_capacity, nsamples_out);
+}
+int mcag_process_packed_f32(mcag_proc p, const float *in, long long in_pitch, int nsamples, float *out, long long out_pitch, int *nsamples_out) {
+  return process_host<float>(p, nullptr, in, in_pitch, nsamples, nullptr, out, out_pitch, (int)(out_pitch > 0x7fffffff ? 0x7fffffff : out_pitch), nsamples_out);
+}
+
+int mcag_process_device_f32(mcag_proc p, const float *d_in, long long in_pitch, int nsamples, float *d_out, long long out_pitch, int *nsamples_out) {
+  if (!p) return mcag_set_error(MCAG_ERR_INVALID, "null handle");
+  CU(cudaSetDevice(p->cfg.device));
+  int T = 0;
+  OK(process_device_core(p, d_in, in_pitch, nsamples, &T));
+  const int nout = T * p->hop;
+  if (p->Cs > 0 && d_out && nout > 0) {
+    if (nout > out_pitch) return mcag_set_error(MCAG_ERR_CAPACITY, "process: output pitch too small");
+    if (p->Cs == p->Cout) {
+      CU(cudaMemcpy2DAsync(d_out, out_pitch * 4, p->out_dev.p, (size_t)nout * 4, (size_t)nout * 4, (size_t)p->B * p->Cs, cudaMemcpyDeviceToDevice, p->stream));
+    } else {
+      CU(cudaMemset2DAsync(d_out, out_pitch * 4, 0, (size_t)nout * 4, (size_t)p->B * p->Cout, p->stream));
+      for (int b = 0; b < p->B; ++b)
+        CU(cudaMemcpy2DAsync(d_out + (long long)b * p->Cout * out_pitch, out_pitch * 4, p->out_dev.as<float>() + (long long)b * p->Cs * nout, (size_t)nout * 4,
+                             (size_t)nout * 4, p->Cs, cudaMemcpyDeviceToDevice, p->stream));
+    }
+  }
+  if (nsamples_out) *nsamples_out = p->Cs > 0 ? nout : 0;
+  return MCAG_OK;
+}
+
+static const DevBuf *result_buf(mcag_proc p, int what) {
+  switch (what) {
+    case MCAG_OUT_SPECTRA: return &p->spec;
+    case MCAG_OUT_POWER_DB: return &p->power_db;
+    case MCAG_OUT_CORR: return &p->corr;
+    case MCAG_OUT_ENERGY: return &p->energy;
+    case MCAG_OUT_CELL: return &p->cells;
+    case MCAG_OUT_PROB: return &p->prob;
+    case MCAG_OUT_LAGS: return &p->lags;
+    case MCAG_OUT_CURVES: return &p->curves;
+    case MCAG_OUT_ACTIVE: return &p->active;
+    case MCAG_OUT_BEAMS: return p->cfg.kind == MCAG_KIND_MASK ? &p->spec : &p->beams;
+    case MCAG_OUT_MASK_Q: return &p->qtrace;
+    case MCAG_OUT_MASK_DEC: return &p->dec;
+  }
+  return nullptr;
+}
+const void *mcag_device_ptr(mcag_proc p, int what) {
+  if (!p) return nullptr;
+  const DevBuf *b = result_buf(p, what);
+  return b ? b->p : nullptr;
+}
+int mcag_fetch(mcag_proc p, int what, void *dst, long long bytes) {
+  if (!p || !dst) return mcag_set_error(MCAG_ERR_INVALID, "null argument");
+  const DevBuf *b = result_buf(p, what);
+  if (!b || !b->p) return mcag_set_error(MCAG_ERR_INVALID, "result not produced by this processor kind / emit flags");
+  if (bytes < 0 || (size_t)bytes > b->bytes) return mcag_set_error(MCAG_ERR_CAPACITY, "fetch: more bytes than the result holds");
+  CU(cudaSetDevice(p->cfg.device));
+  CU(cudaMemcpyAsync(dst, b->p, (size_t)bytes, cudaMemcpyDeviceToHost, p->stream));
+  CU(cudaStreamSynchronize(p->stream));
+  return MCAG_OK;
+}
+
+// ---- kernel-level wrappers ------------------------------------------------------------------------------------------
+int mcag_k_twiddles(int N, void *d_tw, void *stream) {
+  std::vector<float2> tw(N / 2);
+  for (int n = 0; n < N / 2; ++n) { double a = -2.0 * M_PI * (double)n / (double)N; tw[n] = make_float2((float)std::cos(a), (float)std::sin(a)); }
+  CU(cudaMemcpyAsync(d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  return MCAG_OK;
+}
+int mcag_k_phase_fx(const double *h_turns, long long n, uint64_t *d_fx, void *stream) {
+  std::vector<uint64_t> fx((size_t)n);
+  for (long long i = 0; i < n; ++i) fx[(size_t)i] = turns_to_fx(h_turns[i]);
+  CU(cudaMemcpyAsync(d_fx, fx.data(), (size_t)n * 8, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  return MCAG_OK;
+}
+int mcag_k_stft(const float *d_x, long long row_pitch, int rows, int M, int T, int N, int hop, const float *d_win, const void *d_tw, void *d_spec,
+                float *d_chan_pow, void *stream) {
+  return k_stft(d_x, row_pitch, rows, M, T, N, hop, d_win, (const float2 *)d_tw, (float2 *)d_spec, d_chan_pow, (cudaStream_t)stream);
+}
+int mcag_k_istft(const void *d_spec, int B, int T, int C_in, int C_out, int N, int hop, const float *d_win, const void *d_tw, const float *d_tail_in,
+                 float *d_tail_out, float *d_out, long long out_pitch, void *stream) {
+  return k_istft((const float2 *)d_spec, B, T, C_in, C_out, N, hop, d_win, (const float2 *)d_tw, d_tail_in, d_tail_out, d_out, out_pitch, (cudaStream_t)stream);
+}
+int mcag_k_tdoa_lags(const void *d_spec, int B, int T, int M, int N, int max_lag, const void *d_tw, float *d_curves, int32_t *d_lags, float *d_peaks,
+                     void *stream) {
+  return k_tdoa_lags((const float2 *)d_spec, B, T, M, N, max_lag, (const float2 *)d_tw, d_curves, d_lags, d_peaks, (cudaStream_t)stream);
+}
+int mcag_k_gcc_tau(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_pair_fx, int D, float *d_corr, void *stream) {
+  return k_gcc_tau((const float2 *)d_spec, B, T, M, N, d_pair_fx, D, d_corr, (cudaStream_t)stream);
+}
+int mcag_k_pair_sum(const float *d_corr, long long BT, int P, int D, float scale, float *d_esum, void *stream) {
+  return k_pair_sum(d_corr, BT, P, D, scale, d_esum, (cudaStream_t)stream);
+}
+int mcag_k_energy_scan(const float *d_esum, int B, int T, int D, float a, const unsigned char *d_active, float *d_state, float *d_energy, void *stream) {
+  return k_energy_scan(d_esum, B, T, D, a, d_active, d_state, d_energy, (cudaStream_t)stream);
+}
+int mcag_k_select_doa(const float *d_energy, long long BT, int D, int n_pairs, int S, int32_t *d_idx, float *d_prob, void *stream) {
+  return k_select_doa(d_energy, BT, D, n_pairs, S, d_idx, d_prob, (cudaStream_t)stream);
+}
+int mcag_k_ds_fan(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_steer_fx, int D, void *d_out, void *stream) {
+  return k_ds_fan((const float2 *)d_spec, B, T, M, N, d_steer_fx, D, (float2 *)d_out, (cudaStream_t)stream);
+}
+int mcag_k_srp_channel(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_mic_fx, int D, float *d_srp, void *stream) {
+  return k_srp_channel((const float2 *)d_spec, B, T, M, N, d_mic_fx, D, d_srp, (cudaStream_t)stream);
+}
+#ifndef MCAG_HAVE_SRP_TENSOR
+int mcag_k_srp_tensor(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_mic_fx, int D, float *d_srp, void *stream) {
+  return k_srp_channel((const float2 *)d_spec, B, T, M, N, d_mic_fx, D, d_srp, (cudaStream_t)stream);
+}
+#endif
+
+}  // extern "C"

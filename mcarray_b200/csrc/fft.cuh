@@ -1,0 +1,124 @@
+// Shared-memory Stockham FFT engine (complex, NC = 128/256/512/1024 points) for the real FFTs of the STFT,
+// the inverse STFT and the GCC-PHAT lag transform.  NC/8 threads cooperate on one transform; each thread
+// owns 8 points per pass (one radix-8, two radix-4 or four radix-2 butterflies) in registers, passes exchange
+// through a padded float2 buffer in shared memory.  Real N = 2*NC transforms use the packed-complex trick.
+//
+// Twiddles come from a table tw[n] = exp(-2*pi*i*n/N), n < N/2 (= NC entries), computed in double on the host.
+#pragma once
+#include "common.cuh"
+
+namespace mcag {
+
+// buffer index padding: one extra float2 per 8 keeps the stride-8 / stride-64 stores of the radix-8 passes
+// spread over the 16 64-bit bank pairs
+__host__ __device__ constexpr int fft_pad(int i) { return i + (i >> 3); }
+__host__ __device__ constexpr int fft_buf_len(int NC) { return NC + (NC >> 3); }
+
+template <int NC> struct FftPlan;
+template <> struct FftPlan<128>  { static constexpr int NP = 3; static constexpr int R[4] = {8, 8, 2, 1}; };
+template <> struct FftPlan<256>  { static constexpr int NP = 3; static constexpr int R[4] = {8, 8, 4, 1}; };
+template <> struct FftPlan<512>  { static constexpr int NP = 3; static constexpr int R[4] = {8, 8, 8, 1}; };
+template <> struct FftPlan<1024> { static constexpr int NP = 4; static constexpr int R[4] = {8, 8, 8, 2}; };
+
+// sync among the NC/8 threads of one transform: a warp (or less) syncs itself, larger groups use a named barrier
+template <int TPF> __device__ __forceinline__ void group_sync(int group) {
+  if constexpr (TPF == 32) {
+    __syncwarp();
+  } else if constexpr (TPF < 32) {
+    // several transforms share one warp and may diverge from each other: sync only this transform's lanes
+    const unsigned lane = threadIdx.x & 31u;
+    __syncwarp((((1u << TPF) - 1u)) << (lane & ~(unsigned)(TPF - 1)));
+  } else {
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(TPF) : "memory");
+  }
+}
+
+// W_N^(n) for n in [0, N): table holds the first half
+template <bool INV> __device__ __forceinline__ float2 tw_lookup(const float2 *tw, int n, int half) {
+  float2 w = n < half ? tw[n] : tw[n - half];
+  if (n >= half) { w.x = -w.x; w.y = -w.y; }
+  if (INV) w.y = -w.y;
+  return w;
+}
+
+template <bool INV> __device__ __forceinline__ void dft2(float2 &a, float2 &b) {
+  float2 t = a; a = cadd(t, b); b = csub(t, b);
+}
+// multiply by -i (forward) or +i (inverse)
+template <bool INV> __device__ __forceinline__ float2 rot90(float2 a) { return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
+
+template <bool INV> __device__ __forceinline__ void dft4(float2 &v0, float2 &v1, float2 &v2, float2 &v3) {
+  float2 a0 = cadd(v0, v2), a1 = csub(v0, v2), a2 = cadd(v1, v3), a3 = rot90<INV>(csub(v1, v3));
+  v0 = cadd(a0, a2); v2 = csub(a0, a2); v1 = cadd(a1, a3); v3 = csub(a1, a3);
+}
+template <bool INV> __device__ __forceinline__ void dft8(float2 *v) {
+  float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
+  dft4<INV>(e0, e1, e2, e3);
+  dft4<INV>(o0, o1, o2, o3);
+  const float h = 0.70710678118654752440f;
+  // W8^1 = (1 -+ i)/sqrt2, W8^2 = -+i, W8^3 = (-1 -+ i)/sqrt2
+  float2 t1 = INV ? make_float2((o1.x - o1.y) * h, (o1.x + o1.y) * h) : make_float2((o1.x + o1.y) * h, (o1.y - o1.x) * h);
+  float2 t2 = rot90<INV>(o2);
+  float2 t3 = INV ? make_float2((-o3.x - o3.y) * h, (o3.x - o3.y) * h) : make_float2((o3.y - o3.x) * h, (-o3.x - o3.y) * h);
+  v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+  v[1] = cadd(e1, t1); v[5] = csub(e1, t1);
+  v[2] = cadd(e2, t2); v[6] = csub(e2, t2);
+  v[3] = cadd(e3, t3); v[7] = csub(e3, t3);
+}
+
+// One Stockham pass over the 8 points this thread holds.  On entry v[b*R + r] = in[jj_b + r*NC/R] with
+// jj_b = j + b*NC/8; on exit the results are stored to buf at their autosort positions.
+template <int NC, int R, int NS, bool INV>
+__device__ __forceinline__ void fft_pass_store(float2 *v, float2 *buf, const float2 *tw, int j) {
+  constexpr int NB = 8 / R;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const int jj = j + b * (NC / 8);
+    const int k = jj & (NS - 1);
+    float2 *u = v + b * R;
+    if (NS > 1) {
+#pragma unroll
+      for (int r = 1; r < R; ++r) u[r] = cmul(u[r], tw_lookup<INV>(tw, k * r * (2 * NC / (NS * R)), NC));
+    }
+    if constexpr (R == 8) dft8<INV>(u);
+    else if constexpr (R == 4) dft4<INV>(u[0], u[1], u[2], u[3]);
+    else dft2<INV>(u[0], u[1]);
+    const int j0 = (jj - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) buf[fft_pad(j0 + r * NS)] = u[r];
+  }
+}
+template <int NC, int R> __device__ __forceinline__ void fft_pass_load(float2 *v, const float2 *buf, int j) {
+  constexpr int NB = 8 / R;
+#pragma unroll
+  for (int b = 0; b < NB; ++b)
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[b * R + r] = buf[fft_pad(j + b * (NC / 8) + r * (NC / R))];
+}
+
+// Full transform.  The caller has already placed the first pass's inputs in v[] (v[r] = in[j + r*NC/8], the
+// first pass is always radix 8), so loading, windowing and packing fuse into the caller.  On return the
+// spectrum sits in buf (natural order, padded indexing) and the group is synchronised.
+template <int NC, bool INV>
+__device__ __forceinline__ void fft_run(float2 *v, float2 *buf, const float2 *tw, int j, int group) {
+  using P = FftPlan<NC>;
+  constexpr int TPF = NC / 8;
+  fft_pass_store<NC, 8, 1, INV>(v, buf, tw, j);
+  group_sync<TPF>(group);
+  fft_pass_load<NC, P::R[1]>(v, buf, j);
+  group_sync<TPF>(group);
+  fft_pass_store<NC, P::R[1], 8, INV>(v, buf, tw, j);
+  group_sync<TPF>(group);
+  fft_pass_load<NC, P::R[2]>(v, buf, j);
+  group_sync<TPF>(group);
+  fft_pass_store<NC, P::R[2], 8 * P::R[1], INV>(v, buf, tw, j);
+  group_sync<TPF>(group);
+  if constexpr (P::NP == 4) {
+    fft_pass_load<NC, P::R[3]>(v, buf, j);
+    group_sync<TPF>(group);
+    fft_pass_store<NC, P::R[3], 8 * P::R[1] * P::R[2], INV>(v, buf, tw, j);
+    group_sync<TPF>(group);
+  }
+}
+
+}  // namespace mcag

@@ -1,0 +1,42 @@
+// Internal launcher prototypes (device pointers, stream-ordered).  The C ABI in include/mcarray_b200.h wraps these.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mcag {
+
+// stft.cu
+int k_stft(const float *x, long long row_pitch, int rows, int M, int T, int N, int hop, const float *win, const float2 *tw, float2 *spec,
+           float *chan_pow, cudaStream_t st);
+int k_istft(const float2 *spec, int B, int T, int C_in, int C_out, int N, int hop, const float *win, const float2 *tw, const float *tail_in,
+            float *tail_out, float *out, long long out_pitch, cudaStream_t st);
+int k_frame_power(const float2 *spec, long long rows, int N, float *pow, cudaStream_t st);
+
+// gcc.cu
+int k_tdoa_lags(const float2 *spec, int B, int T, int M, int N, int max_lag, const float2 *tw, float *curves, int32_t *lags, float *peaks,
+                cudaStream_t st);
+int k_gcc_tau(const float2 *spec, int B, int T, int M, int N, const uint64_t *pair_fx, int D, float *corr, cudaStream_t st);
+
+// doa.cu
+int k_pair_sum(const float *corr, long long BT, int P, int D, float scale, float *esum, cudaStream_t st);
+int k_energy_scan(const float *esum, int B, int T, int D, float a, const unsigned char *active, float *state, float *energy, cudaStream_t st);
+int k_select_doa(const float *energy, long long BT, int D, int n_pairs, int S, int32_t *idx, float *prob, cudaStream_t st);
+int k_curve_scan_argmax(const float *corr, int B, int T, int D, float keep_first, float mem, const unsigned char *active, float *state,
+                        unsigned char *started, float *curves, int32_t *idx, cudaStream_t st);
+
+// beamform.cu
+int k_steer_table(const uint64_t *fx, int DM, int N, float2 *tab, cudaStream_t st);
+int k_ds_select(const float2 *spec, int B, int T, int M, int N, const float2 *steer_tab, const int32_t *cells, int S, int C_out, float2 *out,
+                cudaStream_t st);
+int k_ds_fan(const float2 *spec, int B, int T, int M, int N, const uint64_t *steer_fx, int D, float2 *out, cudaStream_t st);
+
+// srp.cu
+int k_srp_channel(const float2 *spec, int B, int T, int M, int N, const uint64_t *mic_fx, int D, float *srp, cudaStream_t st);
+
+// mask.cu
+int k_mask_stats(const float2 *spec, long long BT, int N, const float *H2, int nb, float *stats, cudaStream_t st);
+int k_mask_scan(const float *stats, int B, int T, int N, int nb, int method, int alg, const float *thresholds, float *Q, float *noise,
+                int first_call, float *gains, unsigned char *decisions, float *q_trace, cudaStream_t st);
+int k_mask_apply(float2 *spec, long long BT, int N, const float *H, int nb, const float *gains, cudaStream_t st);
+
+}  // namespace mcag

@@ -1,0 +1,148 @@
+// K6 binaural_mask: FastBinauralMasking::processParametrisation and helpers
+// (FastBinauralMasking.cpp:126-538, constants FastBinauralMasking.h:111-128), split into
+//   stats  : per (frame, band) reductions of the band-filtered spectra (H_b is real, so |H_b X|^2 = H_b^2 |X|^2)
+//   scan   : the per-band first-order power tracker over frames plus every mask decision / gain (sequential in t)
+//   apply  : out[k] = X[k] * sum_b gain_b * H_b[k]  (gain only on bins 0..N/2-1, the Nyquist bin is summed unmasked)
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mcag {
+
+constexpr int MS_NSTAT = 6;   // pw2, num, eL, eR, pL, pR
+
+// one CTA per frame.  stats[bt][b][0] = sum_{k<N/2} H2 |(L+R)/2|^2      (getFramePower :496-538)
+//                               [1] = sum_{k<K}   H2 Re(R conj L)        (normaliseFFTCorrelation :437-441)
+//                               [2],[3] = sum_{k<K} H2 |L|^2, |R|^2      (:446-452, maskFrameByScaling :262-264)
+//                               [4],[5] = sum_{k<N/2} H2 |L|^2, |R|^2    (noisyFrame -> getPower :222,520-538)
+__global__ void __launch_bounds__(256) mask_stats_kernel(const float2 *__restrict__ spec, int N, const float *__restrict__ H2, int nb,
+                                                          float *__restrict__ stats) {
+  extern __shared__ float4 s_q[];   // per bin: (|L+R|^2/4, Re(R L*), |L|^2, |R|^2)
+  const int KP = spec_pitch(N), K = N / 2 + 1, NH = N / 2;
+  const long long bt = blockIdx.x;
+  const float2 *L = spec + bt * 2 * KP, *R = L + KP;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float2 l = L[k], r = R[k];
+    const float mx = 0.5f * l.x + 0.5f * r.x, my = 0.5f * l.y + 0.5f * r.y;
+    s_q[k] = make_float4(mx * mx + my * my, r.x * l.x + r.y * l.y, l.x * l.x + l.y * l.y, r.x * r.x + r.y * r.y);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int b = warp; b < nb; b += nwarp) {
+    const float *h = H2 + (size_t)b * KP;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float w = h[k];
+      if (w == 0.f) continue;
+      const float4 q = s_q[k];
+      a1 = fmaf(w, q.y, a1); a2 = fmaf(w, q.z, a2); a3 = fmaf(w, q.w, a3);
+      if (k < NH) { a0 = fmaf(w, q.x, a0); a4 = fmaf(w, q.z, a4); a5 = fmaf(w, q.w, a5); }
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3); a4 = warp_sum(a4); a5 = warp_sum(a5);
+    if (lane == 0) {
+      float *o = stats + (bt * nb + b) * MS_NSTAT;
+      o[0] = a0; o[1] = a1; o[2] = a2; o[3] = a3; o[4] = a4; o[5] = a5;
+    }
+  }
+}
+
+// one thread per (stream, band), sequential over frames.  method / alg enums: ArrayModules.h:81,89.
+__global__ void mask_scan_kernel(const float *__restrict__ stats, int B, int T, int N, int nb, int method, int alg,
+                                 const float *__restrict__ thresholds, float *__restrict__ Qs, float *__restrict__ noise_s,
+                                 int first_call, float *__restrict__ gains, unsigned char *__restrict__ decisions,
+                                 float *__restrict__ q_trace) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * nb) return;
+  const int s = i / nb, b = i - s * nb;
+  const float K = (float)(N / 2 + 1), NH = (float)(N / 2);
+  const float lam = 0.04f, keep = 1.0f - 0.04f, reject = 0.999f, rho = 0.01f;   // FastBinauralMasking.h:114,122,126
+  float Q = Qs[i], noise = noise_s[i];
+  const float thr = thresholds[b];
+  for (int t = 0; t < T; ++t) {
+    const long long bt = (long long)s * T + t;
+    const float *st = stats + (bt * nb + b) * MS_NSTAT;
+    const float pw = sqrtf(st[0] / NH);
+    Q = Q * lam + keep * pw;                                        // temportalMasking :489
+    bool temp = pw < reject * Q;                                    // :492
+    bool spat = false;
+    if (alg == 0 || alg == 1) {                                     // BOTH / SPATIAL :159-166
+      const float num = st[1] / K;
+      float ncorr;
+      if (num == 0.f) ncorr = 0.f;
+      else { const float den = sqrtf((st[2] / K) * (st[3] / K)); ncorr = (den == 0.f) ? 1.f : num / den; }
+      spat = ncorr < thr;                                           // :374
+      if (alg == 1) temp = false;
+    }
+    float gl = 1.f, gr = 1.f;                                       // enhanceFrame: _enhanceFactor = 1
+    const int dec = spat ? 2 : (temp ? 1 : 0);
+    if (dec) {
+      switch (method) {
+        case 3: gl = gr = 1.0f / 1000.0f; break;                    // FULL  :214-217
+        case 0: gl = gr = 1.0f / (spat ? 10.0f : 3.0f); break;      // FACTOR :284-287, .h:117-118
+        case 1: {                                                   // RELATIVE :246-282 (uses the updated Q)
+          if (Q < 1e-10f) gl = gr = sqrtf(rho);
+          else { gl = sqrtf((st[2] / K) * rho / Q); gr = sqrtf((st[3] / K) * rho / Q); }
+        } break;
+        case 4: {                                                   // NOISY :220-243
+          if (first_call >= 2) {
+            const float pl = sqrtf(st[4] / NH), pr = sqrtf(st[5] / NH);
+            gl = pl > 0.f ? noise / pl : 1.f;
+            gr = pr > 0.f ? noise / pr : 1.f;
+          }
+        } break;
+        default: break;
+      }
+    }
+    gains[(bt * nb + b) * 2] = gl;
+    gains[(bt * nb + b) * 2 + 1] = gr;
+    if (decisions) decisions[bt * nb + b] = (unsigned char)dec;
+    if (q_trace) q_trace[bt * nb + b] = Q;
+    ++first_call;                                                   // :193-197
+    if (first_call < 2) noise = Q;
+  }
+  Qs[i] = Q; noise_s[i] = noise;   // the frame counter (_firstCall) is common to all streams and lives on the host
+}
+
+// one CTA per frame, in place
+__global__ void __launch_bounds__(256) mask_apply_kernel(float2 *__restrict__ spec, int N, const float *__restrict__ H, int nb,
+                                                          const float *__restrict__ gains) {
+  extern __shared__ float s_g[];   // [nb][2]
+  const int KP = spec_pitch(N), K = N / 2 + 1, NH = N / 2;
+  const long long bt = blockIdx.x;
+  for (int i = threadIdx.x; i < nb * 2; i += blockDim.x) s_g[i] = gains[bt * nb * 2 + i];
+  __syncthreads();
+  float2 *L = spec + bt * 2 * KP, *R = L + KP;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float wl = 0.f, wr = 0.f;
+    for (int b = 0; b < nb; ++b) {
+      const float h = H[(size_t)b * KP + k];
+      wl = fmaf(h, (k < NH) ? s_g[2 * b] : 1.f, wl);
+      wr = fmaf(h, (k < NH) ? s_g[2 * b + 1] : 1.f, wr);
+    }
+    float2 l = L[k], r = R[k];
+    L[k] = make_float2(l.x * wl, l.y * wl);
+    R[k] = make_float2(r.x * wr, r.y * wr);
+  }
+}
+
+int k_mask_stats(const float2 *spec, long long BT, int N, const float *H2, int nb, float *stats, cudaStream_t st) {
+  if (BT <= 0) return 0;
+  size_t smem = sizeof(float4) * (N / 2 + 1);
+  mask_stats_kernel<<<(unsigned)BT, 256, smem, st>>>(spec, N, H2, nb, stats);
+  MCAG_CHECK_LAUNCH();
+  return 0;
+}
+int k_mask_scan(const float *stats, int B, int T, int N, int nb, int method, int alg, const float *thresholds, float *Q, float *noise,
+                int first_call, float *gains, unsigned char *decisions, float *q_trace, cudaStream_t st) {
+  if (B * nb <= 0 || T <= 0) return 0;
+  mask_scan_kernel<<<(B * nb + 63) / 64, 64, 0, st>>>(stats, B, T, N, nb, method, alg, thresholds, Q, noise, first_call, gains, decisions, q_trace);
+  MCAG_CHECK_LAUNCH();
+  return 0;
+}
+int k_mask_apply(float2 *spec, long long BT, int N, const float *H, int nb, const float *gains, cudaStream_t st) {
+  if (BT <= 0) return 0;
+  mask_apply_kernel<<<(unsigned)BT, 256, sizeof(float) * nb * 2, st>>>(spec, N, H, nb, gains);
+  MCAG_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace mcag

@@ -1,0 +1,262 @@
+// K1 stft_r2c and K7 istft_ola.  Replace DSPONE's STFT::frameAnalysis / frameSynthesis and the
+// framing + overlap-add of ShortTimeProcess::process that every reference processor runs
+// (SourceSeparationAndLocalisation.cpp:51-52, SourceLocalisation.cpp:51-52, BinauralLocalisation.cpp:320-322,
+// FastBinauralMasking.cpp:57; consumer mcabeamf.cpp:112-119).
+#include "fft.cuh"
+#include "kernels.h"
+
+namespace mcag {
+
+// ---------------------------------------------------------------------------------------------------
+// K1: one CTA = F consecutive frames of one (stream, channel) row.  The (F-1)*hop + N samples the frames
+// share are staged once into shared memory by a 1-D bulk async copy (TMA engine), each frame is windowed
+// while it is packed into the N/2-point complex FFT, and the one-sided spectrum is written with its Parseval
+// power.  HBM traffic per frame: hop*4 B in (+ overlap from L2), (N/2+2)*8 B out.
+// ---------------------------------------------------------------------------------------------------
+template <int N, int F, int G>
+__global__ void __launch_bounds__(G *(N / 16)) stft_kernel(const float *__restrict__ x, long long row_pitch, int M, int T, int hop,
+                                                            const float *__restrict__ win, const float2 *__restrict__ tw_g,
+                                                            float2 *__restrict__ spec, float *__restrict__ chan_pow) {
+  constexpr int NC = N / 2, TPF = NC / 8, KP = spec_pitch(N), NT = G * TPF;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float *s_x = reinterpret_cast<float *>(smem_raw);                   // (F-1)*hop_max + N floats, hop <= N
+  float *s_w = s_x + ((F - 1) * N + N);                               // N
+  float2 *s_tw = reinterpret_cast<float2 *>(s_w + N);                 // NC
+  float2 *s_buf = s_tw + NC;                                          // G * fft_buf_len(NC)
+  float *s_red = reinterpret_cast<float *>(s_buf + G * fft_buf_len(NC));   // G * (TPF/32 or 1)
+  __shared__ __align__(8) uint64_t s_bar;
+
+  const int tid = threadIdx.x, row = blockIdx.y, t0 = blockIdx.x * F;
+  const int nf = min(F, T - t0);
+  const int nsamp = (nf - 1) * hop + N;
+  const float *src = x + (long long)row * row_pitch + (long long)t0 * hop;
+
+  const bool bulk = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((nsamp & 3) == 0);
+  if (bulk) {
+    if (tid == 0) { mbar_init(&s_bar, 1); }
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(&s_bar, (uint32_t)nsamp * 4u);
+      bulk_g2s(s_x, src, (uint32_t)nsamp * 4u, &s_bar);
+    }
+  } else {
+    for (int i = tid; i < nsamp; i += NT) s_x[i] = src[i];
+  }
+  for (int i = tid; i < N; i += NT) s_w[i] = win[i];
+  for (int i = tid; i < NC; i += NT) s_tw[i] = tw_g[i];
+  if (bulk) mbar_wait(&s_bar, 0);
+  __syncthreads();
+
+  const int g = tid / TPF, j = tid % TPF;
+  float2 *buf = s_buf + g * fft_buf_len(NC);
+  const int b = row / M, m = row % M;
+
+  for (int f = g; f < F; f += G) {   // uniform trip count per group; inactive frames are skipped as a group
+    if (f < nf) {
+      const float2 *xs = reinterpret_cast<const float2 *>(s_x + f * hop);   // hop is even -> 8-byte aligned
+      const float2 *ws = reinterpret_cast<const float2 *>(s_w);
+      float2 v[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int n = j + r * (NC / 8);
+        float2 a = xs[n], w = ws[n];
+        v[r] = make_float2(a.x * w.x, a.y * w.y);
+      }
+      fft_run<NC, false>(v, buf, s_tw, j, g);
+      // real post-processing: X[k] = E + W^k O, X[NC-k] = conj(E - W^k O)
+      float2 *out = spec + (((long long)b * T + (t0 + f)) * M + m) * KP;
+      float pw = 0.f;
+      for (int k = j; k <= NC / 2; k += TPF) {
+        float2 zk = buf[fft_pad(k)], zn = buf[fft_pad((NC - k) & (NC - 1))];
+        float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+        float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));   // -i/2 (zk - conj zn)
+        float2 w = tw_lookup<false>(s_tw, k, NC);
+        float2 wo = cmul(w, o);
+        float2 xk = cadd(e, wo), xn = cconj(csub(e, wo));
+        if (k == 0) { xk.y = 0.f; xn.y = 0.f; }
+        out[k] = xk;
+        out[NC - k] = xn;
+        const float wk = (k == 0) ? 1.f : 2.f;
+        pw += wk * (xk.x * xk.x + xk.y * xk.y);
+        if (k != NC - k) pw += wk * (xn.x * xn.x + xn.y * xn.y);
+      }
+      if (j == 0) out[NC + 1] = make_float2(0.f, 0.f);   // pad bin
+      // Parseval power of the windowed frame, reduced in a fixed order
+      constexpr int WPF = (TPF + 31) / 32;
+      if constexpr (TPF >= 32) {   // N = 256 packs two transforms per warp: its power comes from frame_power_kernel
+        pw = warp_sum(pw);
+        if (chan_pow) {
+          if ((tid & 31) == 0) s_red[g * WPF + (j >> 5)] = pw;
+          group_sync<TPF>(g);
+          if (j == 0) {
+            float s = 0.f;
+            for (int i = 0; i < WPF; ++i) s += s_red[g * WPF + i];
+            chan_pow[((long long)b * T + (t0 + f)) * M + m] = s / ((float)N * (float)N);
+          }
+        }
+      }
+      group_sync<TPF>(g);
+    }
+  }
+}
+
+// power for the small-TPF case is handled by a dedicated reduction kernel (frame_power_kernel below), which is
+// also the generic path: spec [rows] -> pow[rows], rows = B*T*M.
+__global__ void frame_power_kernel(const float2 *__restrict__ spec, long long rows, int N, float *__restrict__ pow) {
+  const int KP = spec_pitch(N), K = N / 2 + 1;
+  const long long row = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float2 *s = spec + row * KP;
+  float acc = 0.f;
+  for (int k = threadIdx.x & 31; k < K; k += 32) {
+    float2 v = s[k];
+    acc += ((k == 0 || k == K - 1) ? 1.f : 2.f) * (v.x * v.x + v.y * v.y);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) pow[row] = acc / ((float)N * (float)N);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K7: one CTA = F consecutive hop-segments of one (stream, channel) row.  It inverse-transforms the
+// F + R - 1 frames that overlap them (R = N/hop), applies the synthesis window and sums the overlaps in frame
+// order (oldest first, as the reference's overlap-add does).  Segment indices >= T belong to the carried tail.
+// ---------------------------------------------------------------------------------------------------
+template <int N, int F, int G>
+__global__ void __launch_bounds__(G *(N / 16)) istft_kernel(const float2 *__restrict__ spec, int C_in, int C_out, int T, int hop,
+                                                             const float *__restrict__ win, const float2 *__restrict__ tw_g,
+                                                             const float *__restrict__ tail_in, float *__restrict__ tail_out,
+                                                             float *__restrict__ out, long long out_pitch) {
+  constexpr int NC = N / 2, TPF = NC / 8, KP = spec_pitch(N), NT = G * TPF;
+  const int R = N / hop;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float *s_y = reinterpret_cast<float *>(smem_raw);                   // (F + Rmax - 1) * N, Rmax = 4
+  float *s_w = s_y + (F + 3) * N;                                     // N
+  float2 *s_tw = reinterpret_cast<float2 *>(s_w + N);                 // NC
+  float2 *s_buf = s_tw + NC;                                          // G * fft_buf_len(NC)
+  float2 *s_in = s_buf + G * fft_buf_len(NC);                         // G * KP  (staged spectrum rows)
+
+  const int tid = threadIdx.x, row = blockIdx.y, seg0 = blockIdx.x * F;
+  const int b = row / C_out, c = row % C_out;
+  const int nfr = F + R - 1;            // frames seg0-R+1 .. seg0+F-1
+  for (int i = tid; i < N; i += NT) s_w[i] = win[i];
+  for (int i = tid; i < NC; i += NT) s_tw[i] = tw_g[i];
+  __syncthreads();
+
+  const int g = tid / TPF, j = tid % TPF;
+  float2 *buf = s_buf + g * fft_buf_len(NC);
+  float2 *xin = s_in + g * KP;
+  for (int fi = g; fi < nfr; fi += G) {
+    const int t = seg0 - (R - 1) + fi;
+    float *y = s_y + fi * N;
+    if (t < 0 || t >= T) {
+      for (int i = j; i < N; i += TPF) y[i] = 0.f;
+    } else {
+      const float2 *src = spec + (((long long)b * T + t) * C_in + c) * KP;
+      for (int k = j; k < KP; k += TPF) xin[k] = src[k];
+      group_sync<TPF>(g);
+      float2 v[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int k = j + r * (NC / 8);
+        float2 xk = xin[k], xn = xin[NC - k];
+        if (k == 0) { xk.y = 0.f; xn.y = 0.f; }   // c2r ignores the imaginary parts of DC and Nyquist
+        float2 e = make_float2(0.5f * (xk.x + xn.x), 0.5f * (xk.y - xn.y));
+        float2 d = make_float2(0.5f * (xk.x - xn.x), 0.5f * (xk.y + xn.y));   // (xk - conj xn)/2
+        float2 o = cmul(d, tw_lookup<true>(s_tw, k, NC));                      // * conj(W^k)
+        v[r] = make_float2(e.x - o.y, e.y + o.x);                              // E + iO
+      }
+      fft_run<NC, true>(v, buf, s_tw, j, g);
+      const float sc = 1.0f / (float)NC;
+      for (int n = j; n < NC; n += TPF) {
+        float2 z = buf[fft_pad(n)];
+        y[2 * n] = z.x * sc * s_w[2 * n];
+        y[2 * n + 1] = z.y * sc * s_w[2 * n + 1];
+      }
+      group_sync<TPF>(g);
+    }
+  }
+  __syncthreads();
+  // overlap-add, oldest frame first; the carried tail (older still) goes in first of all
+  const int ov = N - hop;
+  for (int i = tid; i < F * hop; i += NT) {
+    const int sl = i / hop, n = i - sl * hop, seg = seg0 + sl;
+    if (seg >= T + R - 1) continue;
+    const long long pos = (long long)seg * hop + n;
+    float acc = (tail_in && pos < ov) ? tail_in[(long long)row * ov + pos] : 0.f;
+    for (int r = R - 1; r >= 0; --r) acc += s_y[(sl + (R - 1) - r) * N + n + r * hop];
+    if (seg < T) out[(long long)row * out_pitch + pos] = acc;
+    else if (tail_out) tail_out[(long long)row * ov + (pos - (long long)T * hop)] = acc;
+  }
+}
+
+template <int N> static int launch_stft(const float *x, long long row_pitch, int rows, int M, int T, int hop, const float *win,
+                                        const float2 *tw, float2 *spec, float *chan_pow, cudaStream_t st) {
+  constexpr int NC = N / 2, TPF = NC / 8;
+  constexpr int G = (TPF >= 128) ? 2 : (256 / TPF);
+  constexpr int F = G > 8 ? G : 8;
+  size_t smem = sizeof(float) * ((F - 1) * N + N) + sizeof(float) * N + sizeof(float2) * NC + sizeof(float2) * G * fft_buf_len(NC) +
+                sizeof(float) * G * 4;
+  auto kern = stft_kernel<N, F, G>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid((T + F - 1) / F, rows);
+  float *pow_in_kernel = (TPF >= 32) ? chan_pow : nullptr;
+  kern<<<grid, G * TPF, smem, st>>>(x, row_pitch, M, T, hop, win, tw, spec, pow_in_kernel);
+  MCAG_CHECK_LAUNCH();
+  if (chan_pow && TPF < 32) {
+    long long nrows = (long long)(rows / M) * T * M;
+    frame_power_kernel<<<(unsigned)((nrows + 7) / 8), 256, 0, st>>>(spec, nrows, N, chan_pow);
+    MCAG_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+template <int N> static int launch_istft(const float2 *spec, int B, int T, int C_in, int C_out, int hop, const float *win, const float2 *tw,
+                                         const float *tail_in, float *tail_out, float *out, long long out_pitch, cudaStream_t st) {
+  constexpr int NC = N / 2, TPF = NC / 8;
+  constexpr int F = 8;
+  constexpr int G = (TPF >= 128) ? 2 : (256 / TPF);
+  size_t smem = sizeof(float) * (F + 3) * N + sizeof(float) * N + sizeof(float2) * NC + sizeof(float2) * G * fft_buf_len(NC) +
+                sizeof(float2) * G * spec_pitch(N);
+  auto kern = istft_kernel<N, F, G>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int R = N / hop;
+  dim3 grid((T + R - 1 + F - 1) / F, B * C_out);
+  kern<<<grid, G * TPF, smem, st>>>(spec, C_in, C_out, T, hop, win, tw, tail_in, tail_out, out, out_pitch);
+  MCAG_CHECK_LAUNCH();
+  return 0;
+}
+
+int k_stft(const float *x, long long row_pitch, int rows, int M, int T, int N, int hop, const float *win, const float2 *tw, float2 *spec,
+           float *chan_pow, cudaStream_t st) {
+  if (T <= 0) return 0;
+  if (hop <= 0 || hop > N || (hop & 1) || (N % hop)) return mcag_set_error(1, "stft: hop must be even and divide N");
+  switch (N) {
+    case 256: return launch_stft<256>(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, st);
+    case 512: return launch_stft<512>(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, st);
+    case 1024: return launch_stft<1024>(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, st);
+    case 2048: return launch_stft<2048>(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, st);
+  }
+  return mcag_set_error(1, "stft: frame size must be 256, 512, 1024 or 2048");
+}
+
+int k_istft(const float2 *spec, int B, int T, int C_in, int C_out, int N, int hop, const float *win, const float2 *tw, const float *tail_in,
+            float *tail_out, float *out, long long out_pitch, cudaStream_t st) {
+  if (T <= 0) return 0;
+  if (hop <= 0 || hop > N || (N % hop) || N / hop > 4) return mcag_set_error(1, "istft: hop must divide N with N/hop <= 4");
+  switch (N) {
+    case 256: return launch_istft<256>(spec, B, T, C_in, C_out, hop, win, tw, tail_in, tail_out, out, out_pitch, st);
+    case 512: return launch_istft<512>(spec, B, T, C_in, C_out, hop, win, tw, tail_in, tail_out, out, out_pitch, st);
+    case 1024: return launch_istft<1024>(spec, B, T, C_in, C_out, hop, win, tw, tail_in, tail_out, out, out_pitch, st);
+    case 2048: return launch_istft<2048>(spec, B, T, C_in, C_out, hop, win, tw, tail_in, tail_out, out, out_pitch, st);
+  }
+  return mcag_set_error(1, "istft: frame size must be 256, 512, 1024 or 2048");
+}
+
+int k_frame_power(const float2 *spec, long long rows, int N, float *pow, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  frame_power_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(spec, rows, N, pow);
+  MCAG_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace mcag

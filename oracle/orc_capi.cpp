@@ -256,16 +256,28 @@ extern "C" void orc_gcc_tau_frames(const double *spec, int T, int M, int N, cons
   }
 }
 
-// config 2: integer-lag TDOA on all pairs.  curves [T][P][2L+1], lags [T][P].
+// config 2: integer-lag TDOA on all pairs.  curves [T][P][2L+1], lags [T][P].  Uses the precomputed tau matrix exactly as
+// SteeringBeamforming drives dsp::GeneralisedCrossCorrelation (precomputeTauMatrix + calculateCorrelationsForPrecomputedTauMatrix,
+// SteeringBeamforming.cpp:84-88,115-122) with tau = -L..L, then wipp::maxidx (first maximum).
 extern "C" void orc_tdoa_lags(const double *spec, int T, int M, int N, int max_lag, double *curves, int *lags) {
   const int ccs = N + 2, K = N / 2 + 1, P = M * (M - 1) / 2, L = 2 * max_lag + 1;
-  std::vector<double> tmp(static_cast<size_t>(L));
+  std::vector<double> tau(static_cast<size_t>(L)), re(static_cast<size_t>(L));
+  for (int l = -max_lag; l <= max_lag; ++l) tau[size_t(l + max_lag)] = double(l);
+  dsp::GeneralisedCrossCorrelation gcc(K, dsp::GeneralisedCrossCorrelation::ONESIDEDFFT);
+  gcc.precomputeTauMatrix(tau.data(), L, K, dsp::GeneralisedCrossCorrelation::ONESIDEDFFT);
+  std::vector<dsp::Complex> cc(static_cast<size_t>(L));
   for (int t = 0; t < T; ++t) {
     int p = 0;
     for (int i = 0; i < M; ++i)
       for (int j = i + 1; j < M; ++j, ++p) {
-        double *c = curves ? curves + (size_t(t) * P + p) * L : tmp.data();
-        lags[size_t(t) * P + p] = gcc_phat_lags(spec + (size_t(t) * M + i) * ccs, spec + (size_t(t) * M + j) * ccs, K, max_lag, c);
+        gcc.calculateCorrelationsForPrecomputedTauMatrix(reinterpret_cast<const dsp::Complex *>(spec + (size_t(t) * M + i) * ccs),
+                                                         reinterpret_cast<const dsp::Complex *>(spec + (size_t(t) * M + j) * ccs), cc.data(), K, L,
+                                                         dsp::GeneralisedCrossCorrelation::ONESIDEDFFT);
+        wipp::real(reinterpret_cast<const wipp::wipp_complex_t *>(cc.data()), re.data(), size_t(L));
+        double mx; size_t idx;
+        wipp::maxidx(re.data(), size_t(L), &mx, &idx);
+        lags[size_t(t) * P + p] = int(idx) - max_lag;
+        if (curves) std::copy(re.begin(), re.end(), curves + (size_t(t) * P + p) * L);
       }
   }
 }

@@ -1,0 +1,231 @@
+"""GPU parity tests (run on the B200 box with -m gpu): every CUDA path is driven through the C ABI and compared with the
+float64 oracle on the same seeded inputs and with the golden fixtures generated from the reference build.
+
+Tolerances (BASELINE.json north_star): integer outputs (TDOA lags, DOA cells, argmax cells, mask decisions) must be
+bit-exact; float outputs must satisfy |gpu - ref| <= 1e-6 + 1e-4 * scale, where scale is the largest magnitude of the
+reference in the same frame (an fp32 FFT cannot hold 1e-4 relative on individual near-zero bins)."""
+import os
+
+import numpy as np
+import pytest
+
+from mcarray_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+RTOL, ATOL = 1e-4, 1e-6
+
+
+def assert_close(a, ref, frame_axes, what=""):
+    a = np.asarray(a); ref = np.asarray(ref)
+    assert a.shape == ref.shape, (what, a.shape, ref.shape)
+    scale = np.max(np.abs(ref), axis=frame_axes, keepdims=True)
+    err = np.abs(a - ref)
+    bad = err > ATOL + RTOL * scale
+    assert not bad.any(), f"{what}: {bad.sum()} of {bad.size} outside tolerance; worst ratio {np.max(err / (ATOL + RTOL * scale)):.3g}"
+
+
+@pytest.fixture(scope="module")
+def mb():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import mcarray_b200
+    return mcarray_b200
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N", [256, 512, 1024, 2048])
+def test_stft_istft_parity(mb, orc, N):
+    rng = np.random.default_rng(N)
+    M, n = 3, 21 * N // 2 + 40
+    x = (rng.standard_normal((M, n)) * 3000).astype(np.float32)
+    p = mb.TdoaEstimator(16000, M, N, 8, max_frames_per_call=64)
+    p.process(x)
+    T = p.frames_done
+    S = orc.stft(x.astype(np.float64), N, N // 2)
+    assert T == S.shape[0] == (n - N) // (N // 2) + 1
+    assert_close(p.spectra()[0], S, (1, 2), f"stft N={N}")
+    # SignalPower::FFTLogPower of each frame
+    assert np.allclose(p.power_db()[0], orc.fft_log_power(S, N), rtol=0, atol=1e-3)
+
+
+def test_tdoa_config2_parity(mb, orc):
+    """BASELINE config 2: 8-mic circular array r = 0.10 m, 48 kHz, N = 1024, 28 pairs, lag window +-28."""
+    fs, N, L = 48000, 1024, 28
+    xyz = scenes.circular_array(8, 0.10)
+    B = 3
+    x = np.stack([scenes.far_field_scene(xyz, fs, 24 * 512 + N, scenes.azimuth_dirs([0.3 + 0.9 * b]), seed=scenes.stream_seed(b)) for b in range(B)])
+    x32 = x.astype(np.float32)
+    p = mb.TdoaEstimator(fs, 8, N, L, n_streams=B, max_frames_per_call=64, emit_curves=True)
+    p.process(x32.reshape(B * 8, -1))
+    lags, curves = p.lags(), p.curves()
+    mism = 0
+    for b in range(B):
+        S = orc.stft(x32[b].astype(np.float64), N, N // 2)
+        rc, rl = orc.tdoa_lags(S, N, L)
+        assert_close(curves[b], rc, (2,), "gcc curves")
+        mism += int(np.sum(lags[b] != rl))
+    assert mism == 0, f"{mism} TDOA lags differ from the oracle"
+
+
+def test_tdoa_streaming_equals_one_shot(mb):
+    fs, N, L = 16000, 512, 12
+    xyz = scenes.circular_array(4, 0.05)
+    x = scenes.far_field_scene(xyz, fs, 9000, scenes.azimuth_dirs([1.0]), seed=5).astype(np.float32)
+    a = mb.TdoaEstimator(fs, 4, N, L, max_frames_per_call=64)
+    a.process(x)
+    want = a.lags()[0]
+    b = mb.TdoaEstimator(fs, 4, N, L, max_frames_per_call=64)
+    got = []
+    for pos in range(0, x.shape[1], 777):
+        b.process(x[:, pos:pos + 777])
+        if b.frames_done:
+            got.append(b.lags()[0])
+    got = np.concatenate(got)
+    assert np.array_equal(got, want)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["ssl_reemc_16k.npz", "ssl_mcbeam_48k.npz"])
+def test_ssl_against_reference_golden(mb, name):
+    """SourceSeparationAndLocalisation (mcbeam's processor) against fixtures produced by the reference's own code."""
+    g = np.load(os.path.join(G, name))
+    fs, S, xyz = int(g["fs"]), int(g["S"]), g["xyz"]
+    x = g["x"].astype(np.float32)
+    p = mb.SourceSeparationAndLocalisation(fs, xyz, S, usePowerFloor=False, max_frames_per_call=64, emit=1)
+    fired = []
+    p.setCallback(lambda doa, prob, power, n: fired.append((doa.copy(), prob.copy(), power)))
+    outs, cells, energy, corr = [], [], [], []
+    chunk = int(g["chunk"])
+    for pos in range(0, x.shape[1], chunk):
+        y = p.process(x[:, pos:pos + chunk])
+        outs.append(y)
+        if p.frames_done:
+            cells.append(p.cells()[0]); energy.append(p.energy()[0]); corr.append(p.corr()[0])
+    out = np.concatenate(outs, axis=1); cells = np.concatenate(cells); energy = np.concatenate(energy); corr = np.concatenate(corr)
+    T = g["doa_deg"].shape[0]
+    assert cells.shape == (T, S) and len(fired) == T
+    # DOA cells bit-exact: the reference reports doaIdx2angle(cell) in degrees
+    step = np.float32(5 * np.pi / 180)
+    ref_cells = np.round((g["doa_deg"] * np.pi / 180 + np.pi / 2) / step).astype(np.int32)
+    assert np.array_equal(cells, ref_cells), f"{np.sum(cells != ref_cells)} DOA cells differ"
+    assert np.allclose(np.array([f[0] for f in fired]), g["doa_deg"], atol=1e-9)
+    assert_close(energy, g["energy"], (1,), "energy map")
+    assert_close(np.array([f[1] for f in fired]), g["prob"], (1,), "prob")
+    assert np.allclose(np.array([f[2] for f in fired]), g["power"], atol=1e-3)
+    if "corr_scaled" in g:
+        assert_close(corr * float(1 - np.float32(0.8)), g["corr_scaled"], (1, 2), "pair correlations")
+    nref = g["out"].shape[1]
+    assert out.shape[1] == nref
+    assert_close(out[: g["out"].shape[0]].T.reshape(-1, p.info.hop, g["out"].shape[0]), g["out"].T.reshape(-1, p.info.hop, g["out"].shape[0]), (1, 2), "separated audio")
+    assert np.all(out[S:] == 0)
+
+
+def test_ssl_power_floor_gate(mb, orc):
+    fs = 16000
+    xyz = scenes.linear_array([0, 0.07, 0.175, 0.21])
+    x = scenes.far_field_scene(xyz, fs, 5 * fs, scenes.azimuth_dirs([np.deg2rad(20)]), seed=5)
+    x[:, : 3 * fs + 4000] *= 1e-3
+    x = x.astype(np.float32)
+    ref = orc.ssl_run(fs, xyz, 1, x.astype(np.float64), chunk=4096, use_floor=True)
+    p = mb.SourceSeparationAndLocalisation(fs, xyz, 1, usePowerFloor=True, max_frames_per_call=64)
+    act, cells, outs = [], [], []
+    for pos in range(0, x.shape[1], 4096):
+        outs.append(p.process(x[:, pos:pos + 4096]))
+        if p.frames_done:
+            act.append(p.active()[0]); cells.append(p.cells()[0])
+    act = np.concatenate(act); cells = np.concatenate(cells); out = np.concatenate(outs, axis=1)
+    assert np.array_equal(np.nonzero(act)[0], ref["fired_frame"])
+    step = np.float32(5 * np.pi / 180)
+    ref_cells = np.round((ref["doa_deg"] * np.pi / 180 + np.pi / 2) / step).astype(np.int32)
+    assert np.array_equal(cells[act.astype(bool)], ref_cells)
+    hop = p.info.hop
+    assert_close(out[:1].T.reshape(-1, hop, 1), ref["out"][:1].T.reshape(-1, hop, 1), (1, 2), "gated separation")
+
+
+def test_freqgcc_against_reference_golden(mb):
+    g = np.load(os.path.join(G, "freqgcc_16k.npz"))
+    x = g["x"].astype(np.float32)
+    p = mb.FreqGCCBinauralLocalisation(int(g["fs"]), float(g["mic_dist"]), usePowerFloor=False, max_frames_per_call=64)
+    curves, idx = [], []
+    for pos in range(0, x.shape[1], int(g["chunk"])):
+        p.process(x[:, pos:pos + int(g["chunk"])])
+        if p.frames_done:
+            curves.append(p.curves()[0]); idx.append(p.cells()[0])
+    curves = np.concatenate(curves); idx = np.concatenate(idx)
+    assert np.array_equal(idx, g["idx"])
+    assert_close(curves, g["curves"], (1,), "smoothed GCC curve")
+
+
+@pytest.mark.parametrize("name,method", [("full", "FULL"), ("relative", "RELATIVE"), ("factor", "FACTOR"), ("noisy", "NOISY")])
+def test_mask_against_reference_golden(mb, name, method):
+    g = np.load(os.path.join(G, "mask_spatial_16k.npz"))
+    x = g["x"].astype(np.float32)
+    p = mb.FastBinauralMasking(int(g["fs"]), float(g["mic_dist"]), float(g["lo"]), float(g["hi"]), method, "BOTH", max_frames_per_call=64)
+    outs, Q = [], []
+    for pos in range(0, x.shape[1], int(g["chunk"])):
+        outs.append(p.process(x[:, pos:pos + int(g["chunk"])]))
+        if p.frames_done:
+            Q.append(p.Q()[0])
+    out = np.concatenate(outs, axis=1); Q = np.concatenate(Q)
+    assert_close(Q, g[f"Q_{name}"], (1,), "short-time band power")
+    ref = g[f"out_{name}"]
+    assert out.shape == ref.shape
+    hop = p.info.hop
+    assert_close(out.T.reshape(-1, hop, 2), ref.T.reshape(-1, hop, 2), (1, 2), f"masked audio ({name})")
+
+
+def test_mask_decisions_vs_oracle(mb, orc):
+    """every boolean mask decision on a broadband two-source scene must match the oracle"""
+    fs, d = 16000, 0.086
+    xyz = scenes.linear_array([0, d])
+    x = scenes.far_field_scene(xyz, fs, 20 * 1024, scenes.azimuth_dirs([0.0, np.deg2rad(60)]), seed=77).astype(np.float32)
+    p = mb.FastBinauralMasking(fs, d, 500, 5000, "RELATIVE", "BOTH", max_frames_per_call=64)
+    p.process(x)
+    dec, spec = p.decisions()[0], p.masked_spectra()[0]
+    N = p.info.window_size
+    S = orc.stft(x.astype(np.float64), N, N // 2)
+    H, fc = orc.mel_bank(N, 45, fs, 500, 5000)
+    ref_spec, ref_dec, _, _ = orc.mask_frames(S, N, fs, d, 1, 0, H, fc)
+    assert np.array_equal(dec.astype(np.int32), ref_dec), f"{np.sum(dec != ref_dec)} decisions differ"
+    assert_close(spec, ref_spec, (1, 2), "masked spectra")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_ds_fan_config3_parity(mb, orc):
+    """BASELINE config 3 (reduced frame count): 32-mic linear array, 0.04 m pitch, 181 azimuths, N = 2048."""
+    fs, N, M = 48000, 2048, 32
+    xyz = scenes.linear_array((np.arange(M) - (M - 1) / 2) * 0.04)
+    doas = np.deg2rad(np.arange(-90, 91, 1.0))
+    x = scenes.far_field_scene(xyz, fs, 5 * 1024 + N, scenes.azimuth_dirs([np.deg2rad(25)]), seed=31).astype(np.float32)
+    p = mb.DelayAndSumFan(fs, xyz, N, doas, max_frames_per_call=16)
+    p.process(x)
+    beams = p.beams()[0]
+    S = orc.stft(x.astype(np.float64), N, N // 2)
+    ref = orc.ds_fan(S, N, fs, xyz[:, 0], doas)
+    assert_close(beams, ref, (1, 2), "beamformed spectra")
+    pw = np.sum(np.abs(beams) ** 2, axis=2).mean(axis=0)
+    assert abs(int(np.argmax(pw)) - (25 + 90)) <= 1     # the fan peaks at the source azimuth
+
+
+def test_srp_config4_parity(mb, orc):
+    """BASELINE config 4 (reduced): 64-mic 8x8 planar array, 3600-direction az x el grid, N = 1024; energy map and argmax."""
+    fs, N = 48000, 1024
+    xyz = scenes.planar_array(8, 8, 0.04)
+    az = np.linspace(-np.pi, np.pi, 120, endpoint=False); el = np.linspace(0.05, 1.45, 30)
+    dirs = scenes.az_el_dirs(az[:, None], el[None, :])
+    src = 57 * 30 + 11
+    x = scenes.far_field_scene(xyz, fs, 3 * 512 + N, dirs[src:src + 1], seed=41).astype(np.float32)
+    p = mb.SrpPhat(fs, xyz, N, dirs, numOfSources=1, max_frames_per_call=8)
+    p.process(x)
+    e = p.energy()[0]
+    S = orc.stft(x.astype(np.float64), N, N // 2)
+    raw = orc.srp_channel(S, N, orc.mic_tau(xyz, fs, dirs), n_threads=8)
+    ref, _ = orc.energy_scan(raw[:, None, :])
+    assert_close(e, ref, (1,), "SRP energy map")
+    assert np.array_equal(np.argmax(e, axis=1), np.argmax(ref, axis=1))
+    assert np.all(np.argmax(e, axis=1) == src)
+    idx, _ = orc.select_doa(ref, 64 * 63 // 2, 1)
+    assert np.array_equal(p.cells()[0], idx)
