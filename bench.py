@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py — channel-samples/s and xRT of the mcarray hot path on B200 (driver contract in the task brief).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg5] [--impl reference]
+
+A "step" is one pass of the hot path over one batch of synthetic multichannel audio:
+  cfg2 (default, the configuration the BASELINE.json metric is quoted on that fits one GPU):
+       B array streams x 8-mic circular array, 48 kHz, N = 1024, hop = 512: STFT -> GCC-PHAT on all 28 pairs ->
+       integer-lag TDOA, T frames per stream per step.
+  cfg5: B streams x 16-mic linear array, 16 kHz, N = 512: SourceSeparationAndLocalisation (STFT -> GCC-PHAT tau grid ->
+       SRP energy -> selectDOA -> delay-and-sum -> overlap-add), the literal mcbeam processor batched over streams.
+Streams are independent, so N > 1 shards them across ranks with no collective (weak scaling: B streams PER GPU).
+
+  value  whole-job channel-samples/s with the input already resident in HBM (mcag_process_device_f32)
+  e2e    the same metric through the host-buffer C-ABI call (mcag_process_packed_f32 from pinned memory + result fetch),
+         host<->device copies inside the timed region
+  roofline      dominant kernel (largest share of the per-kernel CUDA-event times recorded on the handle's stream)
+  cpu_baseline  the float64 oracle (oracle/, checker + CPU baseline only) on a bounded sample, all host cores
+
+--impl reference times the reference's CPU path (the oracle restatement; the reference's own DSPONE/WIPP/FFTW build is
+not available) on the same config.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle", "py")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC, UNIT = "channel_samples_per_sec", "channel-samples/s"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d["bf16_tflops"]), source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# workloads
+# ----------------------------------------------------------------------------------------------------------------------
+class Workload:
+    name = ""
+
+    def scene(self, stream_id, n):
+        raise NotImplementedError
+
+    def host_input(self, rank, B, n, unique=8):
+        """[B*M][n] float32.  `unique` distinct seeded scenes per rank are generated in float64 and rotated in time for the
+        remaining streams (every stream still has its own samples at its own addresses)."""
+        from mcarray_b200 import scenes  # noqa: F401
+        base = [self.scene(rank * B + u, n).astype(np.float32) for u in range(min(unique, B))]
+        x = np.empty((B * self.M, n), dtype=np.float32)
+        for b in range(B):
+            src = base[b % len(base)]
+            x[b * self.M:(b + 1) * self.M] = np.roll(src, 1009 * (b // len(base)), axis=1)
+        return x
+
+
+class Cfg2(Workload):
+    """8-mic circular array GCC-PHAT TDOA on all 28 pairs, 48 kHz, 1024-sample frames (BASELINE.json configs[1])."""
+    name = "cfg2: 8-mic circular array r=0.10 m, GCC-PHAT TDOA on all 28 pairs (lags +-28), 48 kHz, N=1024, hop=512"
+    fs, N, hop, M, max_lag = 48000, 1024, 512, 8, 28
+    B_default, T_default = 64, 750
+    dominant_hint = "tdoa"
+
+    def scene(self, stream_id, n):
+        from mcarray_b200 import scenes
+        xyz = scenes.circular_array(self.M, 0.10)
+        az = -np.pi + 2 * np.pi * ((stream_id * 0.6180339887) % 1.0)
+        return scenes.far_field_scene(xyz, self.fs, n, scenes.azimuth_dirs([az]), seed=scenes.stream_seed(stream_id))
+
+    def make(self, mb, B, T):
+        return mb.TdoaEstimator(self.fs, self.M, self.N, self.max_lag, n_streams=B, max_frames_per_call=T)
+
+    def result_bytes(self, p, B, T):
+        return B * T * p.info.n_pairs * 4
+
+    def fetch_result(self, p):
+        return p.lags()
+
+    # algorithmic (compulsory) HBM bytes per frame per stream for each kernel of the chain, fp32
+    def kernel_bytes_per_frame(self):
+        M, hop, K, P = self.M, self.hop, self.N // 2 + 1, self.M * (self.M - 1) // 2
+        return {"stft": 4 * M * hop + 8 * M * K, "tdoa": 8 * M * K + 4 * P, "stft_gcc": 4 * M * hop + 4 * P}
+
+    def pipeline_bytes_per_frame(self):
+        return 4 * self.M * self.hop + 4 * (self.M * (self.M - 1) // 2)   # production mode, 16 496 B
+
+    def cpu_run(self, orc, x64, n_threads):
+        return orc.tdoa_pipeline(x64, self.N, self.hop, self.max_lag, n_threads=n_threads)
+
+
+class Cfg5(Workload):
+    """1024 independent 16-mic array streams of GCC-PHAT + DS beamforming + overlap-add (BASELINE.json configs[4]): 128 per GPU."""
+    name = "cfg5: 16-mic linear array 0.035 m pitch, SourceSeparationAndLocalisation (GCC-PHAT 37-cell grid + DS + OLA), 16 kHz, N=512, hop=256"
+    fs, N, hop, M = 16000, 512, 256, 16
+    B_default, T_default = 128, 125
+    dominant_hint = "gcc_tau"
+
+    def xyz(self):
+        from mcarray_b200 import scenes
+        return scenes.linear_array((np.arange(self.M) - (self.M - 1) / 2) * 0.035)
+
+    def scene(self, stream_id, n):
+        from mcarray_b200 import scenes
+        az = np.deg2rad(-80 + 5 * (stream_id * 7 % 33))
+        return scenes.far_field_scene(self.xyz(), self.fs, n, scenes.azimuth_dirs([az]), seed=scenes.stream_seed(stream_id))
+
+    def make(self, mb, B, T):
+        return mb.SourceSeparationAndLocalisation(self.fs, self.xyz(), 1, usePowerFloor=False, n_streams=B, max_frames_per_call=T)
+
+    def result_bytes(self, p, B, T):
+        return B * T * 4 + B * T * self.hop * 4
+
+    def fetch_result(self, p):
+        return p.cells()
+
+    def kernel_bytes_per_frame(self):
+        M, hop, K, P, D = self.M, self.hop, self.N // 2 + 1, self.M * (self.M - 1) // 2, 37
+        return {"stft": 4 * M * hop + 8 * M * K, "gcc_tau": 8 * M * K + 4 * P * D, "energy": 4 * P * D + 4 * D, "select_doa": 4 * D + 8,
+                "ds_select": 8 * M * K + 8 * K, "istft": 8 * K + 4 * hop}
+
+    def pipeline_bytes_per_frame(self):
+        return 4 * self.M * self.hop + 4 * (self.M * (self.M - 1) // 2) + 4 * self.hop   # 17 888 B
+
+    def cpu_run(self, orc, x64, n_threads):
+        # one stream per thread, exactly the reference object per stream
+        res = [None] * len(x64)
+
+        def work(i0, i1):
+            for i in range(i0, i1):
+                res[i] = orc.ssl_run(self.fs, self.xyz(), 1, x64[i])["doa_deg"]
+        th = [threading.Thread(target=work, args=(len(x64) * i // n_threads, len(x64) * (i + 1) // n_threads)) for i in range(n_threads)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        return res
+
+
+WORKLOADS = {"cfg2": Cfg2, "cfg5": Cfg5}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc = gpu_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons, pw = [], [], set(), []
+        for line in out.strip().splitlines():
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        load = [s for s, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": float(max(pw))}
+
+
+def profile_read(p, reset=True):
+    from mcarray_b200 import capi
+    n = 14
+    ms = (C.c_double * n)()
+    cnt = (C.c_longlong * n)()
+    capi.check(capi.lib().mcag_profile_read(p.handle, ms, cnt, C.c_int(int(reset))))
+    capi.lib().mcag_profile_name.restype = C.c_char_p
+    return {capi.lib().mcag_profile_name(i).decode(): (ms[i], cnt[i]) for i in range(n) if cnt[i] > 0}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_cpu(wl, args, rank, world, as_reference_arm):
+    """The reference's CPU path (float64 oracle restatement) on a bounded sample of the workload, all host cores."""
+    import orc
+    cores = os.cpu_count() or 1
+    if not args.cpu_frames:
+        args.cpu_frames = 128 if as_reference_arm else 512
+    n = wl.N + (args.cpu_frames - 1) * wl.hop
+    Bc = max(cores, 1) * args.cpu_streams_per_core
+    x = np.stack([wl.scene(10_000 + b % 4, n) for b in range(min(Bc, 4))])
+    x64 = np.ascontiguousarray(np.concatenate([x] * ((Bc + len(x) - 1) // len(x)))[:Bc])
+    units = Bc * wl.M * args.cpu_frames * wl.hop
+    sample = f"{Bc} streams x {wl.M} ch x {args.cpu_frames} frames ({units / 1e6:.1f} M channel-samples) per step, float64, {cores} threads, one stream per thread"
+    if not as_reference_arm:
+        wl.cpu_run(orc, x64[:cores], cores)                     # warm-up (page-in, thread start)
+        t0 = time.perf_counter(); wl.cpu_run(orc, x64, cores); dt = time.perf_counter() - t0
+        return {"value": units / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "seconds": dt}
+    for _ in range(args.warmup):
+        wl.cpu_run(orc, x64[:cores], cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        wl.cpu_run(orc, x64, cores)
+    dt = time.perf_counter() - t0
+    v = units * args.steps / dt
+    return {"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl.name, "streams_per_step": Bc, "frames_per_stream": args.cpu_frames, "note": "bounded sample of the GPU arm's workload"},
+            "xrt_aggregate": (units / wl.M / wl.fs) * args.steps / dt,
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--streams", type=int, default=0, help="array streams per GPU (default: per workload)")
+    ap.add_argument("--frames", type=int, default=0, help="frames per stream per step (default: per workload)")
+    ap.add_argument("--cpu-frames", type=int, default=0, help="frames per stream of the CPU sample (default 512 for cpu_baseline, 128 per step for --impl reference)")
+    ap.add_argument("--cpu-streams-per-core", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3 if args.impl == "b200" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = WORKLOADS[args.workload]()
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        print(json.dumps(run_cpu(wl, args, rank, world, True)), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (mcarray_b200 has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import mcarray_b200 as mb
+    from mcarray_b200 import capi
+
+    B = args.streams or wl.B_default
+    T = args.frames or wl.T_default
+    n = wl.N + (T - 1) * wl.hop
+    rows = B * wl.M
+    units_rank = rows * T * wl.hop                                   # channel-samples consumed per step per rank
+
+    # ---- inputs: pinned host block (e2e arm) + a device-resident copy (value arm) -----------------------------------
+    x = wl.host_input(rank, B, n)
+    pin = torch.empty((rows, n), dtype=torch.float32).pin_memory()
+    pin.numpy()[:] = x
+    del x
+    d_in = pin.to(f"cuda:{local}", non_blocking=False)
+    input_bytes = rows * n * 4
+
+    mb.set_default_device(local)
+    p = wl.make(mb, B, T)
+    stream = torch.cuda.ExternalStream(capi.lib().mcag_stream(p.handle), device=torch.device("cuda", local))
+    d_out = None
+    if p.info.n_out_channels:
+        d_out = torch.empty((B * p.info.n_out_channels, T * wl.hop), dtype=torch.float32, device=f"cuda:{local}")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        p.flush_input()
+        p.process_device(d_in, n, n, d_out, T * wl.hop if d_out is not None else 0)
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: input resident in HBM ---------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    p.synchronize()
+    assert p.frames_done == T, (p.frames_done, T)
+    capi.check(capi.lib().mcag_profile_enable(p.handle, 1)); profile_read(p)
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = p.kernel_launches
+    barrier()
+    if sampler:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    ev1.record(stream)
+    p.synchronize()
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.stop() if sampler else None
+    launches = p.kernel_launches - launches0
+    prof = profile_read(p)
+    capi.check(capi.lib().mcag_profile_enable(p.handle, 0))
+    ms_step = ms_total / args.steps
+    value = units_rank * world / (ms_step * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        out_host = None
+        if p.info.n_out_channels:
+            out_host = torch.empty((B * p.info.n_out_channels, T * wl.hop), dtype=torch.float32).pin_memory()
+        res_bytes = wl.result_bytes(p, B, T)
+        nout = C.c_int(0)
+
+        def step_e2e():
+            p.flush_input()
+            capi.check(capi.lib().mcag_process_packed_f32(p.handle, C.c_void_p(pin.data_ptr()), C.c_longlong(n), C.c_int(n),
+                                                          C.c_void_p(out_host.data_ptr()) if out_host is not None else None,
+                                                          C.c_longlong(T * wl.hop if out_host is not None else 0), C.byref(nout)))
+            return wl.fetch_result(p)
+        for _ in range(args.warmup):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_e2e()
+        e1.record(stream)
+        p.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), wall_ms)) / args.steps
+        e2e = {"value": units_rank * world / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": input_bytes, "d2h_bytes_per_step": int(res_bytes),
+               "ms_per_step": ms_e2e}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------------------------------
+    peaks = measured_peaks()
+    kb = wl.kernel_bytes_per_frame()
+    shares = {k: v[0] for k, v in prof.items()}
+    tot = sum(shares.values()) or 1.0
+    dom = max(shares, key=shares.get)
+    dom_ms, dom_n = prof[dom]
+    per_launch_ms = dom_ms / dom_n
+    bytes_per_launch = kb.get(dom, wl.pipeline_bytes_per_frame()) * B * T
+    achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                "traffic": None, "peak_source": peaks["source"], "algorithmic_bytes_per_launch": bytes_per_launch, "ms_per_launch": per_launch_ms,
+                "kernel_share_of_step": dom_ms / tot,
+                "pipeline": {"algorithmic_bytes_per_frame": wl.pipeline_bytes_per_frame(),
+                             "achieved": wl.pipeline_bytes_per_frame() * B * T / (ms_step * 1e-3) / 1e9,
+                             "frac": wl.pipeline_bytes_per_frame() * B * T / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+                "kernels_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        with open(tr) as f:
+            roofline["traffic"] = json.load(f).get(args.workload, {}).get(dom)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl.name, "streams_per_gpu": B, "frames_per_stream_per_step": T, "samples_per_channel_per_step": n,
+                       "input_bytes_per_gpu": input_bytes, "l2_policy": "inputs larger than L2 (input + intermediates per step >> 126 MB)",
+                       "parallelism": f"independent array streams sharded over {world} GPU(s), no collective"},
+            "xrt_aggregate": (B * world * T * wl.hop / wl.fs) / (ms_step * 1e-3), "xrt_per_stream": (T * wl.hop / wl.fs) / (ms_step * 1e-3),
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+    if e2e:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = run_cpu(wl, args, rank, world, False)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -144,6 +144,17 @@ const void *mcag_device_ptr(mcag_proc p, int what);      /* zero-copy access for
 void *mcag_stream(mcag_proc p);                           /* cudaStream_t the handle launches on */
 long long mcag_kernel_launches(mcag_proc p);              /* kernels launched by this handle since creation */
 
+/* Per-kernel device time, measured with CUDA events recorded on the handle's own stream around each launch group.
+ * ms[i] / count[i] accumulate over process calls while enabled; mcag_profile_read synchronises the stream. */
+enum {
+  MCAG_PROF_STFT = 0, MCAG_PROF_GATE, MCAG_PROF_GCC_TAU, MCAG_PROF_ENERGY, MCAG_PROF_SELECT_DOA, MCAG_PROF_DS_SELECT, MCAG_PROF_ISTFT,
+  MCAG_PROF_CURVE_SCAN, MCAG_PROF_TDOA, MCAG_PROF_DS_FAN, MCAG_PROF_SRP, MCAG_PROF_MASK_STATS, MCAG_PROF_MASK_SCAN, MCAG_PROF_MASK_APPLY,
+  MCAG_PROF_COUNT
+};
+int mcag_profile_enable(mcag_proc p, int on);
+int mcag_profile_read(mcag_proc p, double *ms /* [MCAG_PROF_COUNT] */, long long *count /* [MCAG_PROF_COUNT] */, int reset);
+const char *mcag_profile_name(int id);
+
 /* Pinned host memory helpers for the end-to-end path */
 void *mcag_host_alloc(long long bytes);
 void mcag_host_free(void *ptr);

@@ -4,4 +4,4 @@ The product is libmcarray_b200.so (C ABI: include/mcarray_b200.h) plus the C++ h
 This Python package is the thin ctypes mirror used by the tests and bench.py."""
 from . import _capi as capi  # noqa: F401
 from .processors import (DelayAndSumFan, FastBinauralMasking, FreqGCCBinauralLocalisation, Processor,  # noqa: F401
-                         SourceLocalisation, SourceSeparationAndLocalisation, SrpPhat, TdoaEstimator)
+                         SourceLocalisation, SourceSeparationAndLocalisation, SrpPhat, TdoaEstimator, set_default_device)

@@ -164,7 +164,35 @@ struct mcag_proc_s {
   DevBuf H, H2, thr, stats, gains, Q, noise, dec, qtrace;
   void *pin_in = nullptr, *pin_out = nullptr; size_t pin_in_bytes = 0, pin_out_bytes = 0;
   std::vector<double> h_window;
+  // per-kernel CUDA-event timing (mcag_profile_*): events are recorded on the handle's own stream around each launch
+  struct ProfRec { cudaEvent_t a, b; int id; };
+  bool prof_on = false;
+  std::vector<ProfRec> prof_pending;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[MCAG_PROF_COUNT] = {0};
+  long long prof_n[MCAG_PROF_COUNT] = {0};
 };
+
+namespace {
+struct ProfScope {
+  mcag_proc p; int id; cudaEvent_t a = nullptr, b = nullptr;
+  static cudaEvent_t get(mcag_proc p) {
+    if (!p->prof_pool.empty()) { cudaEvent_t e = p->prof_pool.back(); p->prof_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr; cudaEventCreate(&e); return e;
+  }
+  ProfScope(mcag_proc p_, int id_) : p(p_), id(id_) {
+    if (!p->prof_on) return;
+    a = get(p); b = get(p);
+    cudaEventRecord(a, p->stream);
+  }
+  ~ProfScope() {
+    if (!a) return;
+    cudaEventRecord(b, p->stream);
+    p->prof_pending.push_back({a, b, id});
+  }
+};
+}  // namespace
+#define PROF(id) ProfScope prof_scope_##id(p, id)
 
 static int upload(DevBuf &b, const void *src, size_t bytes, cudaStream_t st) {
   OK(b.alloc(bytes));
@@ -342,6 +370,8 @@ void mcag_destroy(mcag_proc p) {
                    &p->lags, &p->curves, &p->curve_state, &p->started, &p->mic_fx, &p->H, &p->H2, &p->thr, &p->stats, &p->gains, &p->Q,
                    &p->noise, &p->dec, &p->qtrace};
   for (DevBuf *b : all) b->release();
+  for (auto &r : p->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (cudaEvent_t e : p->prof_pool) cudaEventDestroy(e);
   if (p->pin_in) cudaFreeHost(p->pin_in);
   if (p->pin_out) cudaFreeHost(p->pin_out);
   if (p->stream) cudaStreamDestroy(p->stream);
@@ -378,6 +408,32 @@ long long mcag_frames_total(mcag_proc p) { return p ? p->frames_total : 0; }
 void *mcag_stream(mcag_proc p) { return p ? (void *)p->stream : nullptr; }
 long long mcag_kernel_launches(mcag_proc p) { return p ? p->launches : 0; }
 
+static const char *const k_prof_names[MCAG_PROF_COUNT] = {"stft", "gate", "gcc_tau", "energy", "select_doa", "ds_select", "istft", "curve_scan",
+                                                        "tdoa", "ds_fan", "srp", "mask_stats", "mask_scan", "mask_apply"};
+const char *mcag_profile_name(int id) { return (id >= 0 && id < MCAG_PROF_COUNT) ? k_prof_names[id] : ""; }
+int mcag_profile_enable(mcag_proc p, int on) {
+  if (!p) return mcag_set_error(MCAG_ERR_INVALID, "null handle");
+  p->prof_on = on != 0;
+  return MCAG_OK;
+}
+int mcag_profile_read(mcag_proc p, double *ms, long long *count, int reset) {
+  if (!p) return mcag_set_error(MCAG_ERR_INVALID, "null handle");
+  CU(cudaSetDevice(p->cfg.device));
+  CU(cudaStreamSynchronize(p->stream));
+  for (auto &r : p->prof_pending) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { p->prof_ms[r.id] += t; p->prof_n[r.id]++; }
+    p->prof_pool.push_back(r.a); p->prof_pool.push_back(r.b);
+  }
+  p->prof_pending.clear();
+  for (int i = 0; i < MCAG_PROF_COUNT; ++i) {
+    if (ms) ms[i] = p->prof_ms[i];
+    if (count) count[i] = p->prof_n[i];
+    if (reset) { p->prof_ms[i] = 0; p->prof_n[i] = 0; }
+  }
+  return MCAG_OK;
+}
+
 void *mcag_host_alloc(long long bytes) {
   void *ptr = nullptr;
   if (cudaMallocHost(&ptr, (size_t)bytes) != cudaSuccess) { mcag_set_error(MCAG_ERR_NOMEM, "cudaMallocHost failed"); return nullptr; }
@@ -396,73 +452,122 @@ static int run_frames(mcag_proc p, const float *x, long long pitch, int T) {
   const int B = p->B, M = p->M, N = p->N, hop = p->hop, D = p->D, P = p->P, S = p->S, kind = p->cfg.kind;
   const long long BT = (long long)B * T;
   float2 *spec = p->spec.as<float2>();
-  OK(k_stft(x, pitch, p->rows, M, T, N, hop, p->win.as<float>(), p->tw.as<float2>(), spec, p->chan_pow.as<float>(), st));
-  p->launches += (N == 256) ? 2 : 1;
-  if (p->cfg.floor_ccs_power) { OK(k_frame_power_raw(spec, BT * M, N, p->chan_raw.as<float>(), st)); p->launches++; }
-  const int needed = (int)(p->cfg.floor_seconds * (float)p->cfg.sample_rate);
-  gate_kernel<<<(B + 127) / 128, 128, 0, st>>>(p->chan_pow.as<float>(), p->chan_raw.as<float>(), B, T, M, N, p->cfg.use_power_floor,
-                                               p->cfg.floor_ccs_power, p->cfg.noise_margin_db, needed, p->gate.as<GateState>(),
-                                               p->power_db.as<float>(), p->active.as<unsigned char>());
-  MCAG_CHECK_LAUNCH();
-  p->launches++;
-  const unsigned char *active = p->active.as<unsigned char>();
-
-  if (kind == MCAG_KIND_SSL || kind == MCAG_KIND_SL) {
-    OK(k_gcc_tau(spec, B, T, M, N, p->pair_fx.as<uint64_t>(), D, p->corr.as<float>(), st));
-    p->launches += (D <= 40) ? 1 : (D + 63) / 64;
-    const float a = p->cfg.energy_memory, b = 1.0f - p->cfg.energy_memory;   // float arithmetic as SteeringBeamforming.cpp:134,139
-    OK(k_pair_sum(p->corr.as<float>(), BT, P, D, b, p->esum.as<float>(), st));
-    OK(k_energy_scan(p->esum.as<float>(), B, T, D, a, active, p->energy_state.as<float>(), p->energy.as<float>(), st));
-    OK(k_select_doa(p->energy.as<float>(), BT, D, P, S, p->raw_idx.as<int32_t>(), p->raw_prob.as<float>(), st));
-    carry_cells_kernel<<<(B * S + 127) / 128, 128, 0, st>>>(p->raw_idx.as<int32_t>(), p->raw_prob.as<float>(), active, B, T, S,
-                                                            p->cell_state.as<int32_t>(), p->prob_state.as<float>(), p->cells.as<int32_t>(),
-                                                            p->prob.as<float>());
+  {
+    PROF(MCAG_PROF_STFT);
+    OK(k_stft(x, pitch, p->rows, M, T, N, hop, p->win.as<float>(), p->tw.as<float2>(), spec, p->chan_pow.as<float>(), st));
+    p->launches += (N == 256) ? 2 : 1;
+  }
+  {
+    PROF(MCAG_PROF_GATE);
+    if (p->cfg.floor_ccs_power) { OK(k_frame_power_raw(spec, BT * M, N, p->chan_raw.as<float>(), st)); p->launches++; }
+    const int needed = (int)(p->cfg.floor_seconds * (float)p->cfg.sample_rate);
+    gate_kernel<<<(B + 127) / 128, 128, 0, st>>>(p->chan_pow.as<float>(), p->chan_raw.as<float>(), B, T, M, N, p->cfg.use_power_floor,
+                                                 p->cfg.floor_ccs_power, p->cfg.noise_margin_db, needed, p->gate.as<GateState>(),
+                                                 p->power_db.as<float>(), p->active.as<unsigned char>());
     MCAG_CHECK_LAUNCH();
-    p->launches += 4;
-    if (kind == MCAG_KIND_SSL) {
-      OK(k_ds_select(spec, B, T, M, N, p->steer_tab.as<float2>(), p->cells.as<int32_t>(), S, p->Cs, p->beams.as<float2>(), st));
-      OK(k_istft(p->beams.as<float2>(), B, T, p->Cs, p->Cs, N, hop, p->win.as<float>(), p->tw.as<float2>(), p->tail[p->tail_cur].as<float>(),
-                 p->tail[p->tail_cur ^ 1].as<float>(), p->out_dev.as<float>(), (long long)T * hop, st));
-      p->tail_cur ^= 1;
+    p->launches++;
+  }
+  const unsigned char *active = p->active.as<unsigned char>();
+  auto select_and_carry = [&]() -> int {
+    {
+      PROF(MCAG_PROF_SELECT_DOA);
+      OK(k_select_doa(p->energy.as<float>(), BT, D, P, S, p->raw_idx.as<int32_t>(), p->raw_prob.as<float>(), st));
+      carry_cells_kernel<<<(B * S + 127) / 128, 128, 0, st>>>(p->raw_idx.as<int32_t>(), p->raw_prob.as<float>(), active, B, T, S,
+                                                              p->cell_state.as<int32_t>(), p->prob_state.as<float>(), p->cells.as<int32_t>(),
+                                                              p->prob.as<float>());
+      MCAG_CHECK_LAUNCH();
       p->launches += 2;
     }
+    return MCAG_OK;
+  };
+  auto synth = [&](const float2 *src, int C) -> int {
+    PROF(MCAG_PROF_ISTFT);
+    OK(k_istft(src, B, T, C, C, N, hop, p->win.as<float>(), p->tw.as<float2>(), p->tail[p->tail_cur].as<float>(),
+               p->tail[p->tail_cur ^ 1].as<float>(), p->out_dev.as<float>(), (long long)T * hop, st));
+    p->tail_cur ^= 1;
+    p->launches++;
+    return MCAG_OK;
+  };
+
+  if (kind == MCAG_KIND_SSL || kind == MCAG_KIND_SL) {
+    {
+      PROF(MCAG_PROF_GCC_TAU);
+      OK(k_gcc_tau(spec, B, T, M, N, p->pair_fx.as<uint64_t>(), D, p->corr.as<float>(), st));
+      p->launches += (D <= 40) ? 1 : (D + 63) / 64;
+    }
+    {
+      PROF(MCAG_PROF_ENERGY);
+      const float a = p->cfg.energy_memory, b = 1.0f - p->cfg.energy_memory;   // float arithmetic as SteeringBeamforming.cpp:134,139
+      OK(k_pair_sum(p->corr.as<float>(), BT, P, D, b, p->esum.as<float>(), st));
+      OK(k_energy_scan(p->esum.as<float>(), B, T, D, a, active, p->energy_state.as<float>(), p->energy.as<float>(), st));
+      p->launches += 2;
+    }
+    OK(select_and_carry());
+    if (kind == MCAG_KIND_SSL) {
+      {
+        PROF(MCAG_PROF_DS_SELECT);
+        OK(k_ds_select(spec, B, T, M, N, p->steer_tab.as<float2>(), p->cells.as<int32_t>(), S, p->Cs, p->beams.as<float2>(), st));
+        p->launches++;
+      }
+      OK(synth(p->beams.as<float2>(), p->Cs));
+    }
   } else if (kind == MCAG_KIND_FREQGCC) {
-    OK(k_gcc_tau(spec, B, T, 2, N, p->pair_fx.as<uint64_t>(), D, p->corr.as<float>(), st));
-    OK(k_curve_scan_argmax(p->corr.as<float>(), B, T, D, 1.0f, p->cfg.corr_memory, active, p->curve_state.as<float>(),
-                           p->started.as<unsigned char>(), p->curves.as<float>(), p->cells.as<int32_t>(), st));
-    p->launches += ((D <= 40) ? 1 : (D + 63) / 64) + 3;
+    {
+      PROF(MCAG_PROF_GCC_TAU);
+      OK(k_gcc_tau(spec, B, T, 2, N, p->pair_fx.as<uint64_t>(), D, p->corr.as<float>(), st));
+      p->launches += (D <= 40) ? 1 : (D + 63) / 64;
+    }
+    {
+      PROF(MCAG_PROF_CURVE_SCAN);
+      OK(k_curve_scan_argmax(p->corr.as<float>(), B, T, D, 1.0f, p->cfg.corr_memory, active, p->curve_state.as<float>(),
+                             p->started.as<unsigned char>(), p->curves.as<float>(), p->cells.as<int32_t>(), st));
+      p->launches += 3;
+    }
   } else if (kind == MCAG_KIND_TDOA) {
+    PROF(MCAG_PROF_TDOA);
     OK(k_tdoa_lags(spec, B, T, M, N, p->cfg.max_lag, p->tw.as<float2>(), p->curves.p ? p->curves.as<float>() : nullptr, p->lags.as<int32_t>(),
                    nullptr, st));
     p->launches++;
   } else if (kind == MCAG_KIND_DSFAN) {
+    PROF(MCAG_PROF_DS_FAN);
     OK(k_ds_fan(spec, B, T, M, N, p->steer_fx.as<uint64_t>(), D, p->beams.as<float2>(), st));
     p->launches++;
   } else if (kind == MCAG_KIND_SRP) {
-    OK(mcag_k_srp_tensor(spec, B, T, M, N, p->mic_fx.as<uint64_t>(), D, p->esum.as<float>(), st));
-    // the pair sum enters the smoothing scaled by (1 - a), like every pair correlation (SteeringBeamforming.cpp:139)
-    OK(k_pair_sum(p->esum.as<float>(), BT, 1, D, 1.0f - p->cfg.energy_memory, p->energy.as<float>(), st));
-    OK(k_energy_scan(p->energy.as<float>(), B, T, D, p->cfg.energy_memory, active, p->energy_state.as<float>(), p->energy.as<float>(), st));
-    OK(k_select_doa(p->energy.as<float>(), BT, D, P, S, p->raw_idx.as<int32_t>(), p->raw_prob.as<float>(), st));
-    carry_cells_kernel<<<(B * S + 127) / 128, 128, 0, st>>>(p->raw_idx.as<int32_t>(), p->raw_prob.as<float>(), active, B, T, S,
-                                                            p->cell_state.as<int32_t>(), p->prob_state.as<float>(), p->cells.as<int32_t>(),
-                                                            p->prob.as<float>());
-    MCAG_CHECK_LAUNCH();
-    p->launches += 5;
+    {
+      PROF(MCAG_PROF_SRP);
+      OK(mcag_k_srp_tensor(spec, B, T, M, N, p->mic_fx.as<uint64_t>(), D, p->esum.as<float>(), st));
+      p->launches++;
+    }
+    {
+      PROF(MCAG_PROF_ENERGY);
+      // the pair sum enters the smoothing scaled by (1 - a), like every pair correlation (SteeringBeamforming.cpp:139)
+      OK(k_pair_sum(p->esum.as<float>(), BT, 1, D, 1.0f - p->cfg.energy_memory, p->energy.as<float>(), st));
+      OK(k_energy_scan(p->energy.as<float>(), B, T, D, p->cfg.energy_memory, active, p->energy_state.as<float>(), p->energy.as<float>(), st));
+      p->launches += 2;
+    }
+    OK(select_and_carry());
   } else if (kind == MCAG_KIND_MASK) {
     const int nb = p->cfg.n_bands;
     if (p->cfg.mask_method != 5) {   // NOTHING: pass-through (FastBinauralMasking.cpp:130-134)
-      OK(k_mask_stats(spec, BT, N, p->H2.as<float>(), nb, p->stats.as<float>(), st));
-      OK(k_mask_scan(p->stats.as<float>(), B, T, N, nb, p->cfg.mask_method, p->cfg.mask_alg, p->thr.as<float>(), p->Q.as<float>(),
-                     p->noise.as<float>(), (int)(p->frames_total > 2 ? 2 : p->frames_total), p->gains.as<float>(), p->dec.as<unsigned char>(),
-                     p->qtrace.as<float>(), st));
-      OK(k_mask_apply(spec, BT, N, p->H.as<float>(), nb, p->gains.as<float>(), st));
-      p->launches += 3;
+      {
+        PROF(MCAG_PROF_MASK_STATS);
+        OK(k_mask_stats(spec, BT, N, p->H2.as<float>(), nb, p->stats.as<float>(), st));
+        p->launches++;
+      }
+      {
+        PROF(MCAG_PROF_MASK_SCAN);
+        OK(k_mask_scan(p->stats.as<float>(), B, T, N, nb, p->cfg.mask_method, p->cfg.mask_alg, p->thr.as<float>(), p->Q.as<float>(),
+                       p->noise.as<float>(), (int)(p->frames_total > 2 ? 2 : p->frames_total), p->gains.as<float>(), p->dec.as<unsigned char>(),
+                       p->qtrace.as<float>(), st));
+        p->launches++;
+      }
+      {
+        PROF(MCAG_PROF_MASK_APPLY);
+        OK(k_mask_apply(spec, BT, N, p->H.as<float>(), nb, p->gains.as<float>(), st));
+        p->launches++;
+      }
     }
-    OK(k_istft(spec, B, T, 2, 2, N, hop, p->win.as<float>(), p->tw.as<float2>(), p->tail[p->tail_cur].as<float>(),
-               p->tail[p->tail_cur ^ 1].as<float>(), p->out_dev.as<float>(), (long long)T * hop, st));
-    p->tail_cur ^= 1;
-    p->launches++;
+    OK(synth(spec, 2));
   }
   return MCAG_OK;
 }

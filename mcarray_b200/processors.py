@@ -22,10 +22,20 @@ _OUT_DTYPE = {capi.OUT_SPECTRA: np.complex64, capi.OUT_POWER_DB: np.float32, cap
               capi.OUT_ACTIVE: np.uint8, capi.OUT_BEAMS: np.complex64, capi.OUT_MASK_Q: np.float32, capi.OUT_MASK_DEC: np.uint8}
 
 
+_default_device = 0
+
+
+def set_default_device(ordinal):
+    """CUDA device ordinal new processors are created on (one process per GPU: call it with LOCAL_RANK)."""
+    global _default_device
+    _default_device = int(ordinal)
+
+
 class Processor:
     """One C-ABI handle.  Keeps the numpy tables the config points at alive."""
 
     def __init__(self, **kw):
+        kw.setdefault("device", _default_device)
         self._keep = []
         cfg = capi.Config()
         capi.lib().mcag_config_init(C.byref(cfg))
