@@ -154,47 +154,43 @@ WORKLOADS = {"cfg2": Cfg2, "cfg5": Cfg5}
 
 # ----------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region: NVML polled every ~2 ms from a thread (the same counters
+    the nvidia-smi recipe in B200_PROFILING.md prints; nvidia-smi's 100 ms loop is too coarse for a tens-of-ms region)."""
+    BITS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "hw_power_brake": 0x80}
 
     def __init__(self, gpu_index):
-        self.gpu, self.proc = gpu_index, None
+        self.gpu, self.rows, self._stop, self.thread, self.err = gpu_index, [], threading.Event(), None, None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self._stop.is_set():
+                self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), mx, nv.nvmlDeviceGetPowerUsage(h) / 1e3,
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(h), nv.nvmlDeviceGetUtilizationRates(h).gpu))
+                time.sleep(0.002)
+            nv.nvmlShutdown()
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+        time.sleep(0.05)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-            out, _ = self.proc.communicate()
-        sm, mx, reasons, pw = [], [], set(), []
-        for line in out.strip().splitlines():
-            f = [s.strip() for s in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        load = [s for s, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm
-        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
-                "power_w_max": float(max(pw))}
+        self._stop.set()
+        self.thread.join(timeout=5)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"no NVML samples ({self.err})"]}
+        sm = [r[0] for r in self.rows]
+        reasons = sorted({name for r in self.rows for name, bit in self.BITS.items() if r[3] & bit})
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(sm), "power_w_max": float(max(r[2] for r in self.rows)), "how": "NVML polled every ~2 ms during the timed region"}
 
 
 def profile_read(p, reset=True):
@@ -242,7 +238,7 @@ def run_cpu(wl, args, rank, world, as_reference_arm):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))

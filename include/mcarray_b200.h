@@ -70,7 +70,8 @@ enum {
 };
 
 enum {                    /* emit flags: keep optional intermediates of the last call fetchable */
-  MCAG_EMIT_CORR = 1, MCAG_EMIT_CURVES = 2
+  MCAG_EMIT_CORR = 1, MCAG_EMIT_CURVES = 2,
+  MCAG_EMIT_SPECTRA = 4   /* TDOA only: its fused STFT->GCC kernel keeps the spectra on chip unless this is set (every other kind always has them) */
 };
 
 typedef struct {
@@ -161,7 +162,8 @@ void mcag_host_free(void *ptr);
 
 /* ---- kernel-level entry points on DEVICE buffers (what the processors are made of; also used by the parity tests) ----
  * `stream` is a cudaStream_t (NULL = default stream).  Spectra rows have pitch N/2+2 complex bins. */
-int mcag_k_twiddles(int N, void *d_tw /* float2 [N/2] */, void *stream);
+int mcag_k_twiddle_count(int N);                        /* float2 entries of the FFT tables for frame size N */
+int mcag_k_twiddles(int N, void *d_tw /* float2 [mcag_k_twiddle_count(N)] */, void *stream);
 int mcag_k_stft(const float *d_x, long long row_pitch, int rows, int M, int T, int N, int hop, const float *d_win, const void *d_tw,
                 void *d_spec, float *d_chan_pow, void *stream);
 int mcag_k_istft(const void *d_spec, int B, int T, int C_in, int C_out, int N, int hop, const float *d_win, const void *d_tw,
@@ -169,6 +171,9 @@ int mcag_k_istft(const void *d_spec, int B, int T, int C_in, int C_out, int N, i
 int mcag_k_tdoa_lags(const void *d_spec, int B, int T, int M, int N, int max_lag, const void *d_tw, float *d_curves, int32_t *d_lags,
                      float *d_peaks, void *stream);
 int mcag_k_phase_fx(const double *h_turns, long long n, uint64_t *d_fx, void *stream);   /* host turns -> device 0.64 fixed point */
+/* fused STFT -> GCC-PHAT -> integer-lag argmax on sample rows (what MCAG_KIND_TDOA runs); d_spec / d_chan_pow / d_curves may be NULL */
+int mcag_k_stft_tdoa(const float *d_x, long long row_pitch, int B, int T, int M, int N, int hop, int max_lag, const float *d_win, const void *d_tw,
+                     void *d_spec, float *d_chan_pow, float *d_curves, int32_t *d_lags, void *stream);
 int mcag_k_gcc_tau(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_pair_fx, int D, float *d_corr, void *stream);
 int mcag_k_pair_sum(const float *d_corr, long long BT, int P, int D, float scale, float *d_esum, void *stream);
 int mcag_k_energy_scan(const float *d_esum, int B, int T, int D, float a, const unsigned char *d_active, float *d_state, float *d_energy, void *stream);

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libmcarray_b200.so")
 KIND_SSL, KIND_SL, KIND_FREQGCC, KIND_MASK, KIND_TDOA, KIND_DSFAN, KIND_SRP = range(7)
 (OUT_SPECTRA, OUT_POWER_DB, OUT_CORR, OUT_ENERGY, OUT_CELL, OUT_PROB, OUT_LAGS, OUT_CURVES, OUT_ACTIVE, OUT_BEAMS,
  OUT_MASK_Q, OUT_MASK_DEC) = range(12)
-EMIT_CORR, EMIT_CURVES = 1, 2
+EMIT_CORR, EMIT_CURVES, EMIT_SPECTRA = 1, 2, 4
 
 c_dp = C.POINTER(C.c_double)
 

@@ -3,7 +3,7 @@
 // CUDA kernel; there is no CPU fallback (a missing device or a failed launch is an error, never a silent detour).
 #include "../../include/mcarray_b200.h"
 #include "kernels.h"
-#include "common.cuh"
+#include "fft.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -43,27 +43,29 @@ static uint64_t turns_to_fx(double turns) {
 // BinauralLocalisation.cpp:387-404,429-434).  One thread per stream, sequential over the frames of the call.
 struct GateState { double acc; double floor; int samples; int estimated; };
 
-__global__ void gate_kernel(const float *__restrict__ chan_pow, const float *__restrict__ chan_raw, int B, int T, int M, int N, int use_floor,
-                            int ccs_mode, float margin_db, int needed, GateState *__restrict__ gs, float *__restrict__ power_db,
-                            unsigned char *__restrict__ active) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  GateState s = gs[b];
-  const bool estimate = ccs_mode ? true : (use_floor != 0);   // FreqGCC estimates the floor even when it will not use it (:429)
-  for (int t = 0; t < T; ++t) {
-    const float *cp = chan_pow + ((long long)b * T + t) * M;
-    double lin = 0.0;
-    for (int m = 0; m < M; ++m) lin += (double)cp[m];
-    lin /= (double)M;
-    double power;
-    if (!s.estimated && estimate) {
+__global__ void __launch_bounds__(256) gate_kernel(const float *__restrict__ chan_pow, const float *__restrict__ chan_raw, int B, int T, int M, int N,
+                                                   int use_floor, int ccs_mode, float margin_db, int needed, GateState *__restrict__ gs,
+                                                   float *__restrict__ power_db, unsigned char *__restrict__ active) {
+  // one CTA per stream: thread 0 walks the frames that still feed the noise-floor estimate (a strictly sequential
+  // accumulation, at most floor_seconds of audio per stream), then all threads gate the remaining frames in parallel.
+  __shared__ GateState s_state;
+  __shared__ int s_t0;
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    GateState s = gs[b];
+    const bool estimate = ccs_mode ? true : (use_floor != 0);   // FreqGCC estimates the floor even when it will not use it (:429)
+    int t = 0;
+    for (; t < T && !s.estimated && estimate; ++t) {
       if (ccs_mode) {
         const float *cr = chan_raw + ((long long)b * T + t) * M;
         double raw = 0.0;
         for (int m = 0; m < M; ++m) raw += (double)cr[m] / (double)(N + 2);
         s.acc += raw / (double)M * (double)N + 1e-10;
       } else {
-        s.acc += lin * (double)N;
+        const float *cp = chan_pow + ((long long)b * T + t) * M;
+        double lin = 0.0;
+        for (int m = 0; m < M; ++m) lin += (double)cp[m];
+        s.acc += lin / (double)M * (double)N;
       }
       s.samples += N;
       if (s.samples >= needed) {
@@ -72,14 +74,23 @@ __global__ void gate_kernel(const float *__restrict__ chan_pow, const float *__r
         s.acc = 10.0 * log10(s.acc) + (double)margin_db;
       }
       s.floor = s.acc;
-      power = s.floor;
-    } else {
-      power = 10.0 * log10(lin);
+      power_db[(long long)b * T + t] = (float)s.floor;
+      active[(long long)b * T + t] = use_floor ? 0 : 1;   // power == floor here, so `power > floor` is false
     }
-    power_db[(long long)b * T + t] = (float)power;
-    active[(long long)b * T + t] = (power > s.floor || !use_floor) ? 1 : 0;
+    gs[b] = s;
+    s_state = s;
+    s_t0 = t;
   }
-  gs[b] = s;
+  __syncthreads();
+  const double floor_db = s_state.floor;
+  for (int t = s_t0 + threadIdx.x; t < T; t += blockDim.x) {
+    const float *cp = chan_pow + ((long long)b * T + t) * M;
+    double lin = 0.0;
+    for (int m = 0; m < M; ++m) lin += (double)cp[m];
+    const double power = 10.0 * log10(lin / (double)M);
+    power_db[(long long)b * T + t] = (float)power;
+    active[(long long)b * T + t] = (power > floor_db || !use_floor) ? 1 : 0;
+  }
 }
 
 // hold the last active selection on gated-off frames (_currentDOA / _prob persist, BSAL.cpp:87-95)
@@ -130,6 +141,23 @@ int k_frame_power_raw(const float2 *spec, long long rows, int N, float *raw, cud
 }  // namespace mcag
 
 using namespace mcag;
+
+template <int NC> static void fill_thread_twiddles(std::vector<float2> &tw) {
+  using P = FftPlan<NC>;
+  constexpr int N = 2 * NC, TPF = NC / 8;
+  int slot = 0, NS = 8;
+  for (int p = 1; p < P::NP; ++p) {
+    const int R = P::R[p], NB = 8 / R;
+    for (int b = 0; b < NB; ++b)
+      for (int r = 1; r < R; ++r, ++slot)
+        for (int j = 0; j < TPF; ++j) {
+          const int jj = j + b * (NC / 8), k = jj & (NS - 1);
+          const double a = -2.0 * M_PI * (double)(k * r * (2 * NC / (NS * R))) / (double)N;
+          tw[NC + slot * TPF + j] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+    NS *= R;
+  }
+}
 
 // ======================================================================================================================
 struct DevBuf {
@@ -279,13 +307,14 @@ int mcag_create(const mcag_config *cfg, mcag_proc *out) {
   for (int n = 0; n < N; ++n) p->h_window[n] = cfg->window ? cfg->window[n] : std::sqrt(0.5 * (1.0 - std::cos(2.0 * M_PI * n / N)));
   { std::vector<float> w(N); for (int n = 0; n < N; ++n) w[n] = (float)p->h_window[n];
     if ((rc = upload(p->win, w.data(), N * sizeof(float), st))) return fail(rc); CU(cudaStreamSynchronize(st)); }
-  if ((rc = p->tw.alloc(sizeof(float2) * N / 2))) return fail(rc);
+  if ((rc = p->tw.alloc(sizeof(float2) * fft_table_len(N)))) return fail(rc);
   if ((rc = mcag_k_twiddles(N, p->tw.p, st))) return fail(rc);
 
   // FIFO: carried samples (< N) + one call's worth of new samples; a call completing Tmax frames consumes Tmax*hop
   p->fifo_cap = ((long long)N + (long long)(T + 1) * p->hop + 3) & ~3LL;
   for (int i = 0; i < 2; ++i) if ((rc = p->fifo[i].alloc(sizeof(float) * p->rows * p->fifo_cap))) return fail(rc);
-  if ((rc = p->spec.alloc(sizeof(float2) * B * T * M * KP))) return fail(rc);
+  if (kind != MCAG_KIND_TDOA || (cfg->emit & MCAG_EMIT_SPECTRA))
+    if ((rc = p->spec.alloc(sizeof(float2) * B * T * M * KP))) return fail(rc);
   if ((rc = p->chan_pow.alloc(sizeof(float) * B * T * M))) return fail(rc);
   if ((rc = p->power_db.alloc(sizeof(float) * B * T))) return fail(rc);
   if ((rc = p->active.alloc(B * T))) return fail(rc);
@@ -409,7 +438,7 @@ void *mcag_stream(mcag_proc p) { return p ? (void *)p->stream : nullptr; }
 long long mcag_kernel_launches(mcag_proc p) { return p ? p->launches : 0; }
 
 static const char *const k_prof_names[MCAG_PROF_COUNT] = {"stft", "gate", "gcc_tau", "energy", "select_doa", "ds_select", "istft", "curve_scan",
-                                                        "tdoa", "ds_fan", "srp", "mask_stats", "mask_scan", "mask_apply"};
+                                                        "stft_gcc", "ds_fan", "srp", "mask_stats", "mask_scan", "mask_apply"};
 const char *mcag_profile_name(int id) { return (id >= 0 && id < MCAG_PROF_COUNT) ? k_prof_names[id] : ""; }
 int mcag_profile_enable(mcag_proc p, int on) {
   if (!p) return mcag_set_error(MCAG_ERR_INVALID, "null handle");
@@ -452,7 +481,13 @@ static int run_frames(mcag_proc p, const float *x, long long pitch, int T) {
   const int B = p->B, M = p->M, N = p->N, hop = p->hop, D = p->D, P = p->P, S = p->S, kind = p->cfg.kind;
   const long long BT = (long long)B * T;
   float2 *spec = p->spec.as<float2>();
-  {
+  if (kind == MCAG_KIND_TDOA) {
+    // fused STFT -> GCC-PHAT -> lag argmax: the spectra stay in shared memory unless MCAG_EMIT_SPECTRA asks for them
+    PROF(MCAG_PROF_TDOA);
+    OK(k_stft_tdoa(x, pitch, B, T, M, N, hop, p->cfg.max_lag, p->win.as<float>(), p->tw.as<float2>(), p->spec.p ? spec : nullptr,
+                   p->chan_pow.as<float>(), p->curves.p ? p->curves.as<float>() : nullptr, p->lags.as<int32_t>(), st));
+    p->launches++;
+  } else {
     PROF(MCAG_PROF_STFT);
     OK(k_stft(x, pitch, p->rows, M, T, N, hop, p->win.as<float>(), p->tw.as<float2>(), spec, p->chan_pow.as<float>(), st));
     p->launches += (N == 256) ? 2 : 1;
@@ -461,7 +496,7 @@ static int run_frames(mcag_proc p, const float *x, long long pitch, int T) {
     PROF(MCAG_PROF_GATE);
     if (p->cfg.floor_ccs_power) { OK(k_frame_power_raw(spec, BT * M, N, p->chan_raw.as<float>(), st)); p->launches++; }
     const int needed = (int)(p->cfg.floor_seconds * (float)p->cfg.sample_rate);
-    gate_kernel<<<(B + 127) / 128, 128, 0, st>>>(p->chan_pow.as<float>(), p->chan_raw.as<float>(), B, T, M, N, p->cfg.use_power_floor,
+    gate_kernel<<<B, 256, 0, st>>>(p->chan_pow.as<float>(), p->chan_raw.as<float>(), B, T, M, N, p->cfg.use_power_floor,
                                                  p->cfg.floor_ccs_power, p->cfg.noise_margin_db, needed, p->gate.as<GateState>(),
                                                  p->power_db.as<float>(), p->active.as<unsigned char>());
     MCAG_CHECK_LAUNCH();
@@ -523,11 +558,6 @@ static int run_frames(mcag_proc p, const float *x, long long pitch, int T) {
                              p->started.as<unsigned char>(), p->curves.as<float>(), p->cells.as<int32_t>(), st));
       p->launches += 3;
     }
-  } else if (kind == MCAG_KIND_TDOA) {
-    PROF(MCAG_PROF_TDOA);
-    OK(k_tdoa_lags(spec, B, T, M, N, p->cfg.max_lag, p->tw.as<float2>(), p->curves.p ? p->curves.as<float>() : nullptr, p->lags.as<int32_t>(),
-                   nullptr, st));
-    p->launches++;
   } else if (kind == MCAG_KIND_DSFAN) {
     PROF(MCAG_PROF_DS_FAN);
     OK(k_ds_fan(spec, B, T, M, N, p->steer_fx.as<uint64_t>(), D, p->beams.as<float2>(), st));
@@ -769,9 +799,17 @@ int mcag_fetch(mcag_proc p, int what, void *dst, long long bytes) {
 }
 
 // ---- kernel-level wrappers ------------------------------------------------------------------------------------------
+int mcag_k_twiddle_count(int N) { return (N == 256 || N == 512 || N == 1024 || N == 2048) ? fft_table_len(N) : 0; }
 int mcag_k_twiddles(int N, void *d_tw, void *stream) {
-  std::vector<float2> tw(N / 2);
+  if (!mcag_k_twiddle_count(N)) return mcag_set_error(MCAG_ERR_INVALID, "twiddles: frame size must be 256, 512, 1024 or 2048");
+  std::vector<float2> tw(fft_table_len(N));
   for (int n = 0; n < N / 2; ++n) { double a = -2.0 * M_PI * (double)n / (double)N; tw[n] = make_float2((float)std::cos(a), (float)std::sin(a)); }
+  switch (N) {
+    case 256: fill_thread_twiddles<128>(tw); break;
+    case 512: fill_thread_twiddles<256>(tw); break;
+    case 1024: fill_thread_twiddles<512>(tw); break;
+    default: fill_thread_twiddles<1024>(tw); break;
+  }
   CU(cudaMemcpyAsync(d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, (cudaStream_t)stream));
   CU(cudaStreamSynchronize((cudaStream_t)stream));
   return MCAG_OK;
@@ -794,6 +832,10 @@ int mcag_k_istft(const void *d_spec, int B, int T, int C_in, int C_out, int N, i
 int mcag_k_tdoa_lags(const void *d_spec, int B, int T, int M, int N, int max_lag, const void *d_tw, float *d_curves, int32_t *d_lags, float *d_peaks,
                      void *stream) {
   return k_tdoa_lags((const float2 *)d_spec, B, T, M, N, max_lag, (const float2 *)d_tw, d_curves, d_lags, d_peaks, (cudaStream_t)stream);
+}
+int mcag_k_stft_tdoa(const float *d_x, long long row_pitch, int B, int T, int M, int N, int hop, int max_lag, const float *d_win, const void *d_tw,
+                     void *d_spec, float *d_chan_pow, float *d_curves, int32_t *d_lags, void *stream) {
+  return k_stft_tdoa(d_x, row_pitch, B, T, M, N, hop, max_lag, d_win, (const float2 *)d_tw, (float2 *)d_spec, d_chan_pow, d_curves, d_lags, (cudaStream_t)stream);
 }
 int mcag_k_gcc_tau(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_pair_fx, int D, float *d_corr, void *stream) {
   return k_gcc_tau((const float2 *)d_spec, B, T, M, N, d_pair_fx, D, d_corr, (cudaStream_t)stream);

@@ -3,22 +3,40 @@
 // owns 8 points per pass (one radix-8, two radix-4 or four radix-2 butterflies) in registers, passes exchange
 // through a padded float2 buffer in shared memory.  Real N = 2*NC transforms use the packed-complex trick.
 //
-// Twiddles come from a table tw[n] = exp(-2*pi*i*n/N), n < N/2 (= NC entries), computed in double on the host.
+// Twiddles come from two tables computed in double on the host (capi.cu: mcag_k_twiddles), stored back to back:
+//   tw[n]  = exp(-2*pi*i*n/N), n < N/2 (= NC entries): the real <-> packed-complex pre/post-processing
+//   twp[slot][j], j < NC/8: the inter-pass twiddles of thread j, one slot per (pass >= 1, block b, r >= 1).  A thread
+//   multiplies by the same factors in every transform it ever runs, so the table is laid out per thread: a warp reads
+//   consecutive float2 (conflict-free) instead of gathering tw[k*r*stride] (8-way bank conflicts, ncu r1_cfg2_full).
 #pragma once
 #include "common.cuh"
 
 namespace mcag {
 
-// buffer index padding: one extra float2 per 8 keeps the stride-8 / stride-64 stores of the radix-8 passes
-// spread over the 16 64-bit bank pairs
-__host__ __device__ constexpr int fft_pad(int i) { return i + (i >> 3); }
-__host__ __device__ constexpr int fft_buf_len(int NC) { return NC + (NC >> 3); }
+// buffer index swizzle: XOR with bits 3..6 keeps every access pattern of the Stockham passes (stride-8 stores, contiguous
+// loads at stride NC/R, 64*(j>>3)+(j&7) stores) at the ideal two wavefronts per 64-bit warp access for all four sizes
+// (checked exhaustively on the host; the old i + (i>>3) padding cost 3-4 wavefronts on the contiguous loads).
+__host__ __device__ constexpr int fft_pad(int i) { return i ^ ((i >> 3) & 15); }
+__host__ __device__ constexpr int fft_buf_len(int NC) { return NC; }
 
 template <int NC> struct FftPlan;
 template <> struct FftPlan<128>  { static constexpr int NP = 3; static constexpr int R[4] = {8, 8, 2, 1}; };
 template <> struct FftPlan<256>  { static constexpr int NP = 3; static constexpr int R[4] = {8, 8, 4, 1}; };
 template <> struct FftPlan<512>  { static constexpr int NP = 3; static constexpr int R[4] = {8, 8, 8, 1}; };
 template <> struct FftPlan<1024> { static constexpr int NP = 4; static constexpr int R[4] = {8, 8, 8, 2}; };
+
+// slots of the per-thread twiddle table: (8/R) * (R-1) per pass after the first
+template <int NC> __host__ __device__ constexpr int fft_twp_slots() {
+  using P = FftPlan<NC>;
+  int n = 0;
+  for (int p = 1; p < P::NP; ++p) n += (8 / P::R[p]) * (P::R[p] - 1);
+  return n;
+}
+__host__ __device__ constexpr int fft_twp_slots_rt(int NC) {
+  return NC == 128 ? fft_twp_slots<128>() : NC == 256 ? fft_twp_slots<256>() : NC == 512 ? fft_twp_slots<512>() : fft_twp_slots<1024>();
+}
+// float2 entries of the combined table for frame size N: tw[N/2] then twp[slots][N/16]
+__host__ __device__ constexpr int fft_table_len(int N) { return N / 2 + fft_twp_slots_rt(N / 2) * (N / 16); }
 
 // sync among the NC/8 threads of one transform: a warp (or less) syncs itself, larger groups use a named barrier
 template <int TPF> __device__ __forceinline__ void group_sync(int group) {
@@ -68,9 +86,9 @@ template <bool INV> __device__ __forceinline__ void dft8(float2 *v) {
 
 // One Stockham pass over the 8 points this thread holds.  On entry v[b*R + r] = in[jj_b + r*NC/R] with
 // jj_b = j + b*NC/8; on exit the results are stored to buf at their autosort positions.
-template <int NC, int R, int NS, bool INV>
-__device__ __forceinline__ void fft_pass_store(float2 *v, float2 *buf, const float2 *tw, int j) {
-  constexpr int NB = 8 / R;
+template <int NC, int R, int NS, int SLOT0, bool INV>
+__device__ __forceinline__ void fft_pass_store(float2 *v, float2 *buf, const float2 *twp, int j) {
+  constexpr int NB = 8 / R, TPF = NC / 8;
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
     const int jj = j + b * (NC / 8);
@@ -78,7 +96,11 @@ __device__ __forceinline__ void fft_pass_store(float2 *v, float2 *buf, const flo
     float2 *u = v + b * R;
     if (NS > 1) {
 #pragma unroll
-      for (int r = 1; r < R; ++r) u[r] = cmul(u[r], tw_lookup<INV>(tw, k * r * (2 * NC / (NS * R)), NC));
+      for (int r = 1; r < R; ++r) {
+        float2 w = twp[(SLOT0 + b * (R - 1) + (r - 1)) * TPF + j];
+        if (INV) w.y = -w.y;
+        u[r] = cmul(u[r], w);
+      }
     }
     if constexpr (R == 8) dft8<INV>(u);
     else if constexpr (R == 4) dft4<INV>(u[0], u[1], u[2], u[3]);
@@ -99,26 +121,36 @@ template <int NC, int R> __device__ __forceinline__ void fft_pass_load(float2 *v
 // Full transform.  The caller has already placed the first pass's inputs in v[] (v[r] = in[j + r*NC/8], the
 // first pass is always radix 8), so loading, windowing and packing fuse into the caller.  On return the
 // spectrum sits in buf (natural order, padded indexing) and the group is synchronised.
+// `twp` is the per-thread twiddle table (shared memory, [slots][NC/8]).
 template <int NC, bool INV>
-__device__ __forceinline__ void fft_run(float2 *v, float2 *buf, const float2 *tw, int j, int group) {
+__device__ __forceinline__ void fft_run(float2 *v, float2 *buf, const float2 *twp, int j, int group) {
   using P = FftPlan<NC>;
   constexpr int TPF = NC / 8;
-  fft_pass_store<NC, 8, 1, INV>(v, buf, tw, j);
+  constexpr int S1 = 0, S2 = S1 + (8 / P::R[1]) * (P::R[1] - 1), S3 = S2 + (8 / P::R[2]) * (P::R[2] - 1);
+  fft_pass_store<NC, 8, 1, 0, INV>(v, buf, twp, j);
   group_sync<TPF>(group);
   fft_pass_load<NC, P::R[1]>(v, buf, j);
   group_sync<TPF>(group);
-  fft_pass_store<NC, P::R[1], 8, INV>(v, buf, tw, j);
+  fft_pass_store<NC, P::R[1], 8, S1, INV>(v, buf, twp, j);
   group_sync<TPF>(group);
   fft_pass_load<NC, P::R[2]>(v, buf, j);
   group_sync<TPF>(group);
-  fft_pass_store<NC, P::R[2], 8 * P::R[1], INV>(v, buf, tw, j);
+  fft_pass_store<NC, P::R[2], 8 * P::R[1], S2, INV>(v, buf, twp, j);
   group_sync<TPF>(group);
   if constexpr (P::NP == 4) {
     fft_pass_load<NC, P::R[3]>(v, buf, j);
     group_sync<TPF>(group);
-    fft_pass_store<NC, P::R[3], 8 * P::R[1] * P::R[2], INV>(v, buf, tw, j);
+    fft_pass_store<NC, P::R[3], 8 * P::R[1] * P::R[2], S3, INV>(v, buf, twp, j);
     group_sync<TPF>(group);
   }
+}
+
+// copy the combined table (tw then twp) from global to shared memory; the caller syncs
+template <int N> __device__ __forceinline__ void fft_load_tables(float2 *s_tab, const float2 *__restrict__ tab_g, int tid, int nthreads) {
+  constexpr int LEN = fft_table_len(N);
+  const float4 *src = reinterpret_cast<const float4 *>(tab_g);
+  float4 *dst = reinterpret_cast<float4 *>(s_tab);
+  for (int i = tid; i < LEN / 2; i += nthreads) dst[i] = src[i];
 }
 
 }  // namespace mcag

@@ -11,44 +11,39 @@
 namespace mcag {
 
 // ---------------------------------------------------------------------------------------------------
-// integer-lag GCC-PHAT.  One CTA per (frame, stream): the M whitened spectra are staged once in shared
-// memory, then each group of N/16 threads runs one pair at a time:
+// integer-lag GCC-PHAT.  The M whitened spectra of one frame sit in shared memory (s_U); each group of N/16
+// threads runs one pair at a time:
 //   Z[k] = E[k] + i O[k] from G = U_i conj(U_j)  ->  N/2-point inverse complex FFT  ->  r[l]/2 in packed form
 //   S[l] = r[l]/2 + (Re G[0] + (-1)^l Re G[N/2])/2   (one-sided sum of oracle/CONVENTIONS.md C5)
+// followed by the lag-window extraction and a first-maximum argmax (warp shuffles).
+// Two kernels share this pair phase:
+//   tdoa_kernel       spectra come from HBM (kernel-level entry mcag_k_tdoa_lags)
+//   stft_tdoa_kernel  the fused STFT -> GCC-PHAT pipeline of the TDOA processor: frames are read straight from the
+//                     sample rows, windowed and transformed in the same CTA; spectra only leave the SM when asked for.
 // ---------------------------------------------------------------------------------------------------
-template <int N, int G>
-__global__ void __launch_bounds__(G *(N / 16)) tdoa_kernel(const float2 *__restrict__ spec, int T, int M, int max_lag,
-                                                            const float2 *__restrict__ tw_g, float *__restrict__ curves,
-                                                            int32_t *__restrict__ lags, float *__restrict__ peaks) {
-  constexpr int NC = N / 2, TPF = NC / 8, KP = spec_pitch(N), NT = G * TPF;
-  const int P = M * (M - 1) / 2, L = 2 * max_lag + 1;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2 *s_U = reinterpret_cast<float2 *>(smem_raw);                 // M * KP
-  float2 *s_tw = s_U + (size_t)M * KP;                                // NC
-  float2 *s_buf = s_tw + NC;                                          // G * fft_buf_len(NC)
-  float *s_curve = reinterpret_cast<float *>(s_buf + G * fft_buf_len(NC));   // G * L
-  unsigned char *s_pair = reinterpret_cast<unsigned char *>(s_curve + G * L);   // 2 * P
+template <int N, int G> struct TdoaSmem {
+  static constexpr int NC = N / 2, TPF = NC / 8, KP = spec_pitch(N), WPF = (TPF + 31) / 32;
+};
 
-  const int tid = threadIdx.x, t = blockIdx.x, b = blockIdx.y;
-  const float2 *src = spec + ((long long)b * T + t) * M * KP;
-  for (int i = tid; i < M * KP; i += NT) {
-    const int k = i % KP;
-    s_U[i] = (k <= NC) ? whiten(src[i]) : make_float2(0.f, 0.f);
-  }
-  for (int i = tid; i < NC; i += NT) s_tw[i] = tw_g[i];
+template <int N, int G>
+__device__ __forceinline__ void pair_table(unsigned char *s_pair, int M, int P, int tid, int NT) {
   for (int p = tid; p < P; p += NT) {   // pair p -> (i, j), i < j lexicographic (SteeringBeamforming.cpp:63-65)
     int i = 0, rem = p;
     while (rem >= M - 1 - i) { rem -= M - 1 - i; ++i; }
     s_pair[2 * p] = (unsigned char)i;
     s_pair[2 * p + 1] = (unsigned char)(i + 1 + rem);
   }
-  __syncthreads();
+}
 
-  const int g = tid / TPF, j = tid % TPF;
-  float2 *buf = s_buf + g * fft_buf_len(NC);
-  float *curve = s_curve + g * L;
+// all P pairs of the frame whose whitened spectra are in s_U; every thread of the CTA calls it (uniform trip count)
+template <int N, int G>
+__device__ __forceinline__ void tdoa_pairs(const float2 *s_U, const float2 *s_tw, const float2 *s_twp, float2 *buf, float *curve,
+                                           const unsigned char *s_pair, float *s_bv, int *s_bi, int P, int max_lag, int g, int j,
+                                           float *__restrict__ curves_ft, int32_t *__restrict__ lags_ft, float *__restrict__ peaks_ft) {
+  constexpr int NC = N / 2, TPF = NC / 8, KP = spec_pitch(N);
+  const int L = 2 * max_lag + 1;
   const int rounds = (P + G - 1) / G;
-  for (int it = 0; it < rounds; ++it) {   // uniform trip count: every thread runs every round, stores are predicated
+  for (int it = 0; it < rounds; ++it) {   // every thread runs every round, stores are predicated
     const int p = it * G + g;
     const bool live = p < P;
     const int pc = live ? p : P - 1;
@@ -64,7 +59,7 @@ __global__ void __launch_bounds__(G *(N / 16)) tdoa_kernel(const float2 *__restr
       float2 o = cmul(d, tw_lookup<true>(s_tw, k, NC));
       v[r] = make_float2(e.x - o.y, e.y + o.x);
     }
-    fft_run<NC, true>(v, buf, s_tw, j, g);
+    fft_run<NC, true>(v, buf, s_twp, j, g);
     const float g0 = Ui[0].x * Uj[0].x, gny = Ui[NC].x * Uj[NC].x;   // both spectra are real at DC / Nyquist
     float best = -3.0e38f; int besti = 0x7fffffff;
     for (int c = j; c < L; c += TPF) {
@@ -79,34 +74,162 @@ __global__ void __launch_bounds__(G *(N / 16)) tdoa_kernel(const float2 *__restr
     if constexpr (TPF >= 32) {
       warp_argmax(best, besti);
       constexpr int WPF = TPF / 32;
-      __shared__ float s_bv[G * (WPF > 0 ? WPF : 1)];
-      __shared__ int s_bi[G * (WPF > 0 ? WPF : 1)];
-      if ((tid & 31) == 0) { s_bv[g * WPF + (j >> 5)] = best; s_bi[g * WPF + (j >> 5)] = besti; }
+      if ((threadIdx.x & 31) == 0) { s_bv[g * WPF + (j >> 5)] = best; s_bi[g * WPF + (j >> 5)] = besti; }
       group_sync<TPF>(g);
       if (j == 0 && live) {
         float bv = s_bv[g * WPF]; int bi = s_bi[g * WPF];
         for (int w = 1; w < WPF; ++w) { float ov = s_bv[g * WPF + w]; int oi = s_bi[g * WPF + w]; if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; } }
-        lags[((long long)b * T + t) * P + p] = bi - max_lag;
-        if (peaks) peaks[((long long)b * T + t) * P + p] = bv;
+        lags_ft[p] = bi - max_lag;
+        if (peaks_ft) peaks_ft[p] = bv;
       }
     } else {
+      const unsigned gmask = ((1u << (TPF & 31)) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(TPF - 1));
 #pragma unroll
       for (int o = TPF / 2; o > 0; o >>= 1) {   // stays inside the aligned TPF-lane segment
-        float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        float ov = __shfl_xor_sync(gmask, best, o);
+        int oi = __shfl_xor_sync(gmask, besti, o);
         if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
       }
       if (j == 0 && live) {
-        lags[((long long)b * T + t) * P + p] = besti - max_lag;
-        if (peaks) peaks[((long long)b * T + t) * P + p] = best;
+        lags_ft[p] = besti - max_lag;
+        if (peaks_ft) peaks_ft[p] = best;
       }
       group_sync<TPF>(g);
     }
-    if (curves && live) {
-      float *dst = curves + (((long long)b * T + t) * P + p) * L;
+    if (curves_ft && live) {
+      float *dst = curves_ft + (size_t)p * L;
       for (int c = j; c < L; c += TPF) dst[c] = curve[c];
     }
     group_sync<TPF>(g);
+  }
+}
+
+template <int N, int G>
+__global__ void __launch_bounds__(G *(N / 16)) tdoa_kernel(const float2 *__restrict__ spec, int T, int M, int max_lag,
+                                                            const float2 *__restrict__ tw_g, float *__restrict__ curves,
+                                                            int32_t *__restrict__ lags, float *__restrict__ peaks) {
+  constexpr int NC = N / 2, TPF = NC / 8, KP = spec_pitch(N), NT = G * TPF, WPF = (TPF + 31) / 32;
+  const int P = M * (M - 1) / 2, L = 2 * max_lag + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *s_U = reinterpret_cast<float2 *>(smem_raw);                 // M * KP
+  float2 *s_tw = s_U + (size_t)M * KP;                                // fft_table_len(N): tw[NC] then twp
+  float2 *s_twp = s_tw + NC;
+  float2 *s_buf = s_tw + fft_table_len(N);                            // G * fft_buf_len(NC)
+  float *s_curve = reinterpret_cast<float *>(s_buf + G * fft_buf_len(NC));   // G * L
+  float *s_bv = s_curve + G * L;                                      // G * WPF
+  int *s_bi = reinterpret_cast<int *>(s_bv + G * WPF);                // G * WPF
+  unsigned char *s_pair = reinterpret_cast<unsigned char *>(s_bi + G * WPF);   // 2 * P
+
+  const int tid = threadIdx.x, t = blockIdx.x, b = blockIdx.y;
+  const float2 *src = spec + ((long long)b * T + t) * M * KP;
+  for (int i = tid; i < M * KP; i += NT) {
+    const int k = i % KP;
+    s_U[i] = (k <= NC) ? whiten(src[i]) : make_float2(0.f, 0.f);
+  }
+  fft_load_tables<N>(s_tw, tw_g, tid, NT);
+  pair_table<N, G>(s_pair, M, P, tid, NT);
+  __syncthreads();
+  const int g = tid / TPF, j = tid % TPF;
+  const long long ft = (long long)b * T + t;
+  tdoa_pairs<N, G>(s_U, s_tw, s_twp, s_buf + g * fft_buf_len(NC), s_curve + g * L, s_pair, s_bv, s_bi, P, max_lag, g, j,
+                   curves ? curves + ft * P * L : nullptr, lags + ft * P, peaks ? peaks + ft * P : nullptr);
+}
+
+// Fused STFT -> GCC-PHAT -> lag argmax.  Persistent CTAs walk the (stream, frame) list; per frame a CTA
+//   1. reads the M windows of N samples straight from the sample rows (coalesced 8-byte loads, the overlapping half is an
+//      L2 hit of the neighbouring frame), applies the analysis window while packing into the N/2-point complex FFT,
+//   2. post-processes to the one-sided spectrum, optionally writes it (and always its Parseval power), whitens it into s_U,
+//   3. runs the pair phase above.
+// Compulsory HBM traffic per frame: 4*M*hop bytes in, 4*P bytes out (+ 8*M*(N/2+2) when spectra are requested).
+template <int N, int G>
+__global__ void __launch_bounds__(G *(N / 16)) stft_tdoa_kernel(const float *__restrict__ x, long long row_pitch, int B, int T, int M, int hop,
+                                                                 int max_lag, const float *__restrict__ win, const float2 *__restrict__ tw_g,
+                                                                 float2 *__restrict__ spec, float *__restrict__ chan_pow,
+                                                                 float *__restrict__ curves, int32_t *__restrict__ lags) {
+  constexpr int NC = N / 2, TPF = NC / 8, KP = spec_pitch(N), NT = G * TPF, WPF = (TPF + 31) / 32;
+  const int P = M * (M - 1) / 2, L = 2 * max_lag + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *s_U = reinterpret_cast<float2 *>(smem_raw);                 // M * KP
+  float2 *s_tw = s_U + (size_t)M * KP;                                // fft_table_len(N)
+  float2 *s_twp = s_tw + NC;
+  float2 *s_buf = s_tw + fft_table_len(N);                            // G * NC
+  float2 *s_w = s_buf + G * fft_buf_len(NC);                          // NC (window, pairs of samples)
+  float *s_curve = reinterpret_cast<float *>(s_w + NC);               // G * L
+  float *s_bv = s_curve + G * L;                                      // G * WPF
+  int *s_bi = reinterpret_cast<int *>(s_bv + G * WPF);                // G * WPF
+  unsigned char *s_pair = reinterpret_cast<unsigned char *>(s_bi + G * WPF);   // 2 * P
+
+  const int tid = threadIdx.x;
+  fft_load_tables<N>(s_tw, tw_g, tid, NT);
+  for (int i = tid; i < NC; i += NT) s_w[i] = make_float2(win[2 * i], win[2 * i + 1]);
+  pair_table<N, G>(s_pair, M, P, tid, NT);
+  __syncthreads();
+  const int g = tid / TPF, j = tid % TPF;
+  float2 *buf = s_buf + g * fft_buf_len(NC);
+  const bool vec_ok = ((row_pitch & 1) == 0) && ((hop & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
+  const long long nframes = (long long)B * T;
+
+  for (long long ft = blockIdx.x; ft < nframes; ft += gridDim.x) {
+    const int b = (int)(ft / T), t = (int)(ft - (long long)b * T);
+    // ---- analysis: channels m = g, g + G, ...
+    for (int m = g; m < M; m += G) {
+      const float *src = x + ((long long)b * M + m) * row_pitch + (long long)t * hop;
+      float2 v[8];
+      if (vec_ok) {
+        const float2 *s2 = reinterpret_cast<const float2 *>(src);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v[r] = __ldg(s2 + j + r * TPF);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) { const int n = j + r * TPF; v[r] = make_float2(src[2 * n], src[2 * n + 1]); }
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) { const float2 w = s_w[j + r * TPF]; v[r].x *= w.x; v[r].y *= w.y; }
+      fft_run<NC, false>(v, buf, s_twp, j, g);
+      // real post-processing: X[k] = E + W^k O, X[NC-k] = conj(E - W^k O)
+      float2 *U = s_U + (size_t)m * KP;
+      float2 *out = spec ? spec + ((ft * M + m) * KP) : nullptr;
+      float pw = 0.f;
+      for (int k = j; k <= NC / 2; k += TPF) {
+        float2 zk = buf[fft_pad(k)], zn = buf[fft_pad((NC - k) & (NC - 1))];
+        float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+        float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));   // -i/2 (zk - conj zn)
+        float2 w = tw_lookup<false>(s_tw, k, NC);
+        float2 wo = cmul(w, o);
+        float2 xk = cadd(e, wo), xn = cconj(csub(e, wo));
+        if (k == 0) { xk.y = 0.f; xn.y = 0.f; }
+        if (out) { out[k] = xk; out[NC - k] = xn; }
+        const float wk = (k == 0) ? 1.f : 2.f;
+        pw += wk * (xk.x * xk.x + xk.y * xk.y);
+        if (k != NC - k) pw += wk * (xn.x * xn.x + xn.y * xn.y);
+        U[k] = whiten(xk);
+        U[NC - k] = whiten(xn);
+      }
+      if (j == 0 && out) out[NC + 1] = make_float2(0.f, 0.f);   // pad bin
+      if (chan_pow) {   // Parseval power of the windowed frame, fixed reduction order
+        if constexpr (TPF >= 32) {
+          pw = warp_sum(pw);
+          if ((tid & 31) == 0) s_bv[g * WPF + (j >> 5)] = pw;
+          group_sync<TPF>(g);
+          if (j == 0) {
+            float sacc = 0.f;
+            for (int i = 0; i < WPF; ++i) sacc += s_bv[g * WPF + i];
+            chan_pow[ft * M + m] = sacc / ((float)N * (float)N);
+          }
+        } else {
+          // several transforms share a warp and a neighbour group may be idle this round: shuffle only among this group's lanes
+          const unsigned gmask = (TPF >= 32) ? 0xffffffffu : (((1u << (TPF & 31)) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(TPF - 1)));
+#pragma unroll
+          for (int o2 = TPF / 2; o2 > 0; o2 >>= 1) pw += __shfl_xor_sync(gmask, pw, o2);
+          if (j == 0) chan_pow[ft * M + m] = pw / ((float)N * (float)N);
+        }
+      }
+      group_sync<TPF>(g);
+    }
+    __syncthreads();
+    tdoa_pairs<N, G>(s_U, s_tw, s_twp, buf, s_curve + g * L, s_pair, s_bv, s_bi, P, max_lag, g, j,
+                     curves ? curves + ft * P * L : nullptr, lags + ft * P, nullptr);
+    __syncthreads();
   }
 }
 
@@ -115,11 +238,36 @@ template <int N> static int launch_tdoa(const float2 *spec, int B, int T, int M,
   constexpr int NC = N / 2, TPF = NC / 8;
   constexpr int G = (TPF >= 128) ? 2 : (256 / TPF);
   const int P = M * (M - 1) / 2, L = 2 * max_lag + 1;
-  size_t smem = sizeof(float2) * ((size_t)M * spec_pitch(N) + NC + (size_t)G * fft_buf_len(NC)) + sizeof(float) * G * L + 2 * P + 16;
+  size_t smem = sizeof(float2) * ((size_t)M * spec_pitch(N) + fft_table_len(N) + (size_t)G * fft_buf_len(NC)) + sizeof(float) * G * L +
+                8 * G * ((TPF + 31) / 32) + 2 * P + 16;
   if (smem > 220 * 1024) return mcag_set_error(1, "tdoa: M*N too large for the shared-memory staged kernel");
   auto kern = tdoa_kernel<N, G>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   kern<<<dim3(T, B), G * TPF, smem, st>>>(spec, T, M, max_lag, tw, curves, lags, peaks);
+  MCAG_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int N> static int launch_stft_tdoa(const float *x, long long row_pitch, int B, int T, int M, int hop, int max_lag, const float *win,
+                                             const float2 *tw, float2 *spec, float *chan_pow, float *curves, int32_t *lags, cudaStream_t st) {
+  constexpr int NC = N / 2, TPF = NC / 8;
+  constexpr int G = (TPF >= 128) ? 4 : (256 / TPF);
+  const int P = M * (M - 1) / 2, L = 2 * max_lag + 1;
+  size_t smem = sizeof(float2) * ((size_t)M * spec_pitch(N) + fft_table_len(N) + (size_t)G * fft_buf_len(NC) + NC) + sizeof(float) * G * L +
+                8 * G * ((TPF + 31) / 32) + 2 * P + 16;
+  if (smem > 220 * 1024) return mcag_set_error(1, "tdoa: M*N too large for the shared-memory staged kernel");
+  auto kern = stft_tdoa_kernel<N, G>;
+  static int sm_count = 0, dev_cached = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != dev_cached) { cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); dev_cached = dev; }
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, G * TPF, smem);
+  if (per_sm < 1) per_sm = 1;
+  const long long nframes = (long long)B * T;
+  const long long grid = nframes < (long long)sm_count * per_sm ? nframes : (long long)sm_count * per_sm;
+  kern<<<(unsigned)grid, G * TPF, smem, st>>>(x, row_pitch, B, T, M, hop, max_lag, win, tw, spec, chan_pow, curves, lags);
   MCAG_CHECK_LAUNCH();
   return 0;
 }
@@ -134,6 +282,21 @@ int k_tdoa_lags(const float2 *spec, int B, int T, int M, int N, int max_lag, con
     case 512: return launch_tdoa<512>(spec, B, T, M, max_lag, tw, curves, lags, peaks, st);
     case 1024: return launch_tdoa<1024>(spec, B, T, M, max_lag, tw, curves, lags, peaks, st);
     case 2048: return launch_tdoa<2048>(spec, B, T, M, max_lag, tw, curves, lags, peaks, st);
+  }
+  return mcag_set_error(1, "tdoa: frame size must be 256, 512, 1024 or 2048");
+}
+
+int k_stft_tdoa(const float *x, long long row_pitch, int B, int T, int M, int N, int hop, int max_lag, const float *win, const float2 *tw,
+                float2 *spec, float *chan_pow, float *curves, int32_t *lags, cudaStream_t st) {
+  if (T <= 0 || B <= 0) return 0;
+  if (M < 2 || M > 255) return mcag_set_error(1, "tdoa: need 2..255 channels");
+  if (max_lag < 0 || max_lag > N / 2 - 1) return mcag_set_error(1, "tdoa: max_lag out of range");
+  if (hop <= 0 || hop > N) return mcag_set_error(1, "tdoa: bad hop");
+  switch (N) {
+    case 256: return launch_stft_tdoa<256>(x, row_pitch, B, T, M, hop, max_lag, win, tw, spec, chan_pow, curves, lags, st);
+    case 512: return launch_stft_tdoa<512>(x, row_pitch, B, T, M, hop, max_lag, win, tw, spec, chan_pow, curves, lags, st);
+    case 1024: return launch_stft_tdoa<1024>(x, row_pitch, B, T, M, hop, max_lag, win, tw, spec, chan_pow, curves, lags, st);
+    case 2048: return launch_stft_tdoa<2048>(x, row_pitch, B, T, M, hop, max_lag, win, tw, spec, chan_pow, curves, lags, st);
   }
   return mcag_set_error(1, "tdoa: frame size must be 256, 512, 1024 or 2048");
 }

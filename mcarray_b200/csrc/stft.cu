@@ -21,8 +21,9 @@ __global__ void __launch_bounds__(G *(N / 16)) stft_kernel(const float *__restri
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float *s_x = reinterpret_cast<float *>(smem_raw);                   // (F-1)*hop_max + N floats, hop <= N
   float *s_w = s_x + ((F - 1) * N + N);                               // N
-  float2 *s_tw = reinterpret_cast<float2 *>(s_w + N);                 // NC
-  float2 *s_buf = s_tw + NC;                                          // G * fft_buf_len(NC)
+  float2 *s_tw = reinterpret_cast<float2 *>(s_w + N);                 // fft_table_len(N): tw[NC] then twp
+  float2 *s_twp = s_tw + NC;                                          // per-thread inter-pass twiddles
+  float2 *s_buf = s_tw + fft_table_len(N);                            // G * fft_buf_len(NC)
   float *s_red = reinterpret_cast<float *>(s_buf + G * fft_buf_len(NC));   // G * (TPF/32 or 1)
   __shared__ __align__(8) uint64_t s_bar;
 
@@ -43,7 +44,7 @@ __global__ void __launch_bounds__(G *(N / 16)) stft_kernel(const float *__restri
     for (int i = tid; i < nsamp; i += NT) s_x[i] = src[i];
   }
   for (int i = tid; i < N; i += NT) s_w[i] = win[i];
-  for (int i = tid; i < NC; i += NT) s_tw[i] = tw_g[i];
+  fft_load_tables<N>(s_tw, tw_g, tid, NT);
   if (bulk) mbar_wait(&s_bar, 0);
   __syncthreads();
 
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(G *(N / 16)) stft_kernel(const float *__restri
         float2 a = xs[n], w = ws[n];
         v[r] = make_float2(a.x * w.x, a.y * w.y);
       }
-      fft_run<NC, false>(v, buf, s_tw, j, g);
+      fft_run<NC, false>(v, buf, s_twp, j, g);
       // real post-processing: X[k] = E + W^k O, X[NC-k] = conj(E - W^k O)
       float2 *out = spec + (((long long)b * T + (t0 + f)) * M + m) * KP;
       float pw = 0.f;
@@ -131,15 +132,16 @@ __global__ void __launch_bounds__(G *(N / 16)) istft_kernel(const float2 *__rest
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float *s_y = reinterpret_cast<float *>(smem_raw);                   // (F + Rmax - 1) * N, Rmax = 4
   float *s_w = s_y + (F + 3) * N;                                     // N
-  float2 *s_tw = reinterpret_cast<float2 *>(s_w + N);                 // NC
-  float2 *s_buf = s_tw + NC;                                          // G * fft_buf_len(NC)
+  float2 *s_tw = reinterpret_cast<float2 *>(s_w + N);                 // fft_table_len(N): tw[NC] then twp
+  float2 *s_twp = s_tw + NC;                                          // per-thread inter-pass twiddles
+  float2 *s_buf = s_tw + fft_table_len(N);                            // G * fft_buf_len(NC)
   float2 *s_in = s_buf + G * fft_buf_len(NC);                         // G * KP  (staged spectrum rows)
 
   const int tid = threadIdx.x, row = blockIdx.y, seg0 = blockIdx.x * F;
   const int b = row / C_out, c = row % C_out;
   const int nfr = F + R - 1;            // frames seg0-R+1 .. seg0+F-1
   for (int i = tid; i < N; i += NT) s_w[i] = win[i];
-  for (int i = tid; i < NC; i += NT) s_tw[i] = tw_g[i];
+  fft_load_tables<N>(s_tw, tw_g, tid, NT);
   __syncthreads();
 
   const int g = tid / TPF, j = tid % TPF;
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(G *(N / 16)) istft_kernel(const float2 *__rest
         float2 o = cmul(d, tw_lookup<true>(s_tw, k, NC));                      // * conj(W^k)
         v[r] = make_float2(e.x - o.y, e.y + o.x);                              // E + iO
       }
-      fft_run<NC, true>(v, buf, s_tw, j, g);
+      fft_run<NC, true>(v, buf, s_twp, j, g);
       const float sc = 1.0f / (float)NC;
       for (int n = j; n < NC; n += TPF) {
         float2 z = buf[fft_pad(n)];
@@ -194,7 +196,7 @@ template <int N> static int launch_stft(const float *x, long long row_pitch, int
   constexpr int NC = N / 2, TPF = NC / 8;
   constexpr int G = (TPF >= 128) ? 2 : (256 / TPF);
   constexpr int F = G > 8 ? G : 8;
-  size_t smem = sizeof(float) * ((F - 1) * N + N) + sizeof(float) * N + sizeof(float2) * NC + sizeof(float2) * G * fft_buf_len(NC) +
+  size_t smem = sizeof(float) * ((F - 1) * N + N) + sizeof(float) * N + sizeof(float2) * fft_table_len(N) + sizeof(float2) * G * fft_buf_len(NC) +
                 sizeof(float) * G * 4;
   auto kern = stft_kernel<N, F, G>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -215,7 +217,7 @@ template <int N> static int launch_istft(const float2 *spec, int B, int T, int C
   constexpr int NC = N / 2, TPF = NC / 8;
   constexpr int F = 8;
   constexpr int G = (TPF >= 128) ? 2 : (256 / TPF);
-  size_t smem = sizeof(float) * (F + 3) * N + sizeof(float) * N + sizeof(float2) * NC + sizeof(float2) * G * fft_buf_len(NC) +
+  size_t smem = sizeof(float) * (F + 3) * N + sizeof(float) * N + sizeof(float2) * fft_table_len(N) + sizeof(float2) * G * fft_buf_len(NC) +
                 sizeof(float2) * G * spec_pitch(N);
   auto kern = istft_kernel<N, F, G>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -241,10 +241,11 @@ class FastBinauralMasking(Processor):
 class TdoaEstimator(Processor):
     """BASELINE config 2: integer-lag GCC-PHAT on all pairs (tau-vector mode of dsp::GeneralisedCrossCorrelation with integer taus)."""
 
-    def __init__(self, sampleRate, n_channels, frame_size, max_lag, n_streams=1, max_frames_per_call=256, emit_curves=False, hop=None):
+    def __init__(self, sampleRate, n_channels, frame_size, max_lag, n_streams=1, max_frames_per_call=256, emit_curves=False, hop=None,
+                 emit_spectra=False):
         super().__init__(kind=capi.KIND_TDOA, sample_rate=sampleRate, frame_size=frame_size, hop=hop or frame_size // 2, n_channels=n_channels,
                          n_streams=n_streams, max_frames_per_call=max_frames_per_call, max_lag=max_lag,
-                         emit=capi.EMIT_CURVES if emit_curves else 0)
+                         emit=(capi.EMIT_CURVES if emit_curves else 0) | (capi.EMIT_SPECTRA if emit_spectra else 0))
         self.max_lag = max_lag
 
     def lags(self):

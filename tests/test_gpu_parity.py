@@ -36,12 +36,18 @@ def mb():
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", ["stft_kernel", "fused_stft_gcc"])
 @pytest.mark.parametrize("N", [256, 512, 1024, 2048])
-def test_stft_istft_parity(mb, orc, N):
+def test_stft_istft_parity(mb, orc, N, path):
+    """K1 spectra of both analysis paths: the TMA-staged stft_kernel every processor runs, and the fused STFT->GCC kernel
+    of the TDOA processor (spectra emitted on request)."""
     rng = np.random.default_rng(N)
     M, n = 3, 21 * N // 2 + 40
     x = (rng.standard_normal((M, n)) * 3000).astype(np.float32)
-    p = mb.TdoaEstimator(16000, M, N, 8, max_frames_per_call=64)
+    if path == "stft_kernel":
+        p = mb.DelayAndSumFan(16000, scenes.linear_array([0.0, 0.05, 0.1]), N, np.array([0.0, 0.3]), max_frames_per_call=64)
+    else:
+        p = mb.TdoaEstimator(16000, M, N, 8, max_frames_per_call=64, emit_spectra=True)
     p.process(x)
     T = p.frames_done
     S = orc.stft(x.astype(np.float64), N, N // 2)
