@@ -110,15 +110,6 @@ __global__ void carry_cells_kernel(const int32_t *__restrict__ raw_idx, const fl
   cell_state[i] = c; prob_state[i] = p;
 }
 
-__global__ void s16_to_f32_kernel(const int16_t *__restrict__ in, float *__restrict__ out, long long n) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (float)in[i];
-}
-__global__ void f64_to_f32_kernel(const double *__restrict__ in, float *__restrict__ out, long long n) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (float)in[i];
-}
-
 int k_frame_power_raw(const float2 *spec, long long rows, int N, float *raw, cudaStream_t st);   // below
 
 __global__ void frame_raw_kernel(const float2 *__restrict__ spec, long long rows, int N, float *__restrict__ raw) {
@@ -178,7 +169,8 @@ struct mcag_proc_s {
   mcag_config cfg;
   int B, M, N, hop, K, KP, P, D, S, Cs /* synthesised channels */, Cout /* channels the caller sees */, Tmax, L;
   int rows;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t ev_in[8] = {nullptr}, ev_done[8] = {nullptr};
   long long launches = 0, frames_total = 0;
   int frames_last = 0;
   // input FIFO (ping-pong), per row capacity fifo_cap floats, fill = carried samples (same for every row)
@@ -299,6 +291,11 @@ int mcag_create(const mcag_config *cfg, mcag_proc *out) {
   int rc = MCAG_OK;
   auto fail = [&](int code) { mcag_destroy(p); return code; };
   if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(mcag_set_error(MCAG_ERR_CUDA, "stream creation failed"));
+  if (cudaStreamCreateWithFlags(&p->copy_in, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&p->copy_out, cudaStreamNonBlocking) != cudaSuccess)
+    return fail(mcag_set_error(MCAG_ERR_CUDA, "stream creation failed"));
+  for (int i = 0; i < 8; ++i)
+    if (cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&p->ev_done[i], cudaEventDisableTiming) != cudaSuccess)
+      return fail(mcag_set_error(MCAG_ERR_CUDA, "event creation failed"));
   cudaStream_t st = p->stream;
   const size_t B = p->B, M = p->M, T = p->Tmax, KP = p->KP, D = p->D, P = p->P, S = p->S;
 
@@ -393,6 +390,8 @@ void mcag_destroy(mcag_proc p) {
   if (!p) return;
   cudaSetDevice(p->cfg.device);
   if (p->stream) cudaStreamSynchronize(p->stream);
+  if (p->copy_in) cudaStreamSynchronize(p->copy_in);
+  if (p->copy_out) cudaStreamSynchronize(p->copy_out);
   DevBuf *all[] = {&p->fifo[0], &p->fifo[1], &p->stage_in, &p->stage_out, &p->win, &p->tw, &p->spec, &p->chan_pow, &p->chan_raw, &p->power_db,
                    &p->active, &p->gate, &p->pair_fx, &p->corr, &p->esum, &p->energy, &p->energy_state, &p->raw_idx, &p->raw_prob, &p->cells,
                    &p->prob, &p->cell_state, &p->prob_state, &p->steer_fx, &p->steer_tab, &p->beams, &p->tail[0], &p->tail[1], &p->out_dev,
@@ -403,6 +402,9 @@ void mcag_destroy(mcag_proc p) {
   for (cudaEvent_t e : p->prof_pool) cudaEventDestroy(e);
   if (p->pin_in) cudaFreeHost(p->pin_in);
   if (p->pin_out) cudaFreeHost(p->pin_out);
+  for (int i = 0; i < 8; ++i) { if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]); if (p->ev_done[i]) cudaEventDestroy(p->ev_done[i]); }
+  if (p->copy_in) cudaStreamDestroy(p->copy_in);
+  if (p->copy_out) cudaStreamDestroy(p->copy_out);
   if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
 }
@@ -476,124 +478,137 @@ void mcag_host_free(void *ptr) { if (ptr) cudaFreeHost(ptr); }
 // the frame pipeline: T complete frames are available at `x` (device, rows x pitch); results land in the handle's arrays,
 // synthesised audio (if any) in out_dev [B*Cs][T*hop]
 // ----------------------------------------------------------------------------------------------------------------------
-static int run_frames(mcag_proc p, const float *x, long long pitch, int T) {
+// Streams [b0, b0 + nb) of the handle; every result / state array is stream-major, so a sub-batch is a pointer offset.
+// process_host uses this to overlap the host->device copy of one group of streams with the kernels of the previous one.
+static int run_frames(mcag_proc p, const float *x_all, long long pitch, int T, int b0, int nb) {
   cudaStream_t st = p->stream;
-  const int B = p->B, M = p->M, N = p->N, hop = p->hop, D = p->D, P = p->P, S = p->S, kind = p->cfg.kind;
-  const long long BT = (long long)B * T;
-  float2 *spec = p->spec.as<float2>();
+  const int B = nb, M = p->M, N = p->N, hop = p->hop, D = p->D, P = p->P, S = p->S, kind = p->cfg.kind, KP = p->KP, Cs = p->Cs;
+  const long long BT = (long long)B * T, o = b0;   // o: stream offset
+  const float *x = x_all + o * M * pitch;
+  float2 *spec = p->spec.p ? p->spec.as<float2>() + o * T * M * KP : nullptr;
+  float *chan_pow = p->chan_pow.as<float>() + o * T * M;
+  float *chan_raw = p->chan_raw.p ? p->chan_raw.as<float>() + o * T * M : nullptr;
+  unsigned char *active = p->active.as<unsigned char>() + o * T;
+  const float *win = p->win.as<float>();
+  const float2 *tw = p->tw.as<float2>();
   if (kind == MCAG_KIND_TDOA) {
     // fused STFT -> GCC-PHAT -> lag argmax: the spectra stay in shared memory unless MCAG_EMIT_SPECTRA asks for them
     PROF(MCAG_PROF_TDOA);
-    OK(k_stft_tdoa(x, pitch, B, T, M, N, hop, p->cfg.max_lag, p->win.as<float>(), p->tw.as<float2>(), p->spec.p ? spec : nullptr,
-                   p->chan_pow.as<float>(), p->curves.p ? p->curves.as<float>() : nullptr, p->lags.as<int32_t>(), st));
+    OK(k_stft_tdoa(x, pitch, B, T, M, N, hop, p->cfg.max_lag, win, tw, spec, chan_pow,
+                   p->curves.p ? p->curves.as<float>() + o * T * P * p->L : nullptr, p->lags.as<int32_t>() + o * T * P, st));
     p->launches++;
   } else {
     PROF(MCAG_PROF_STFT);
-    OK(k_stft(x, pitch, p->rows, M, T, N, hop, p->win.as<float>(), p->tw.as<float2>(), spec, p->chan_pow.as<float>(), st));
+    OK(k_stft(x, pitch, B * M, M, T, N, hop, win, tw, spec, chan_pow, st));
     p->launches += (N == 256) ? 2 : 1;
   }
   {
     PROF(MCAG_PROF_GATE);
-    if (p->cfg.floor_ccs_power) { OK(k_frame_power_raw(spec, BT * M, N, p->chan_raw.as<float>(), st)); p->launches++; }
+    if (p->cfg.floor_ccs_power) { OK(k_frame_power_raw(spec, BT * M, N, chan_raw, st)); p->launches++; }
     const int needed = (int)(p->cfg.floor_seconds * (float)p->cfg.sample_rate);
-    gate_kernel<<<B, 256, 0, st>>>(p->chan_pow.as<float>(), p->chan_raw.as<float>(), B, T, M, N, p->cfg.use_power_floor,
-                                                 p->cfg.floor_ccs_power, p->cfg.noise_margin_db, needed, p->gate.as<GateState>(),
-                                                 p->power_db.as<float>(), p->active.as<unsigned char>());
+    gate_kernel<<<B, 256, 0, st>>>(chan_pow, chan_raw, B, T, M, N, p->cfg.use_power_floor, p->cfg.floor_ccs_power, p->cfg.noise_margin_db, needed,
+                                   p->gate.as<GateState>() + o, p->power_db.as<float>() + o * T, active);
     MCAG_CHECK_LAUNCH();
     p->launches++;
   }
-  const unsigned char *active = p->active.as<unsigned char>();
+  float *energy = p->energy.p ? p->energy.as<float>() + o * T * D : nullptr;
+  float *esum = p->esum.p ? p->esum.as<float>() + o * T * D : nullptr;
+  float *energy_state = p->energy_state.p ? p->energy_state.as<float>() + o * D : nullptr;
   auto select_and_carry = [&]() -> int {
-    {
-      PROF(MCAG_PROF_SELECT_DOA);
-      OK(k_select_doa(p->energy.as<float>(), BT, D, P, S, p->raw_idx.as<int32_t>(), p->raw_prob.as<float>(), st));
-      carry_cells_kernel<<<(B * S + 127) / 128, 128, 0, st>>>(p->raw_idx.as<int32_t>(), p->raw_prob.as<float>(), active, B, T, S,
-                                                              p->cell_state.as<int32_t>(), p->prob_state.as<float>(), p->cells.as<int32_t>(),
-                                                              p->prob.as<float>());
-      MCAG_CHECK_LAUNCH();
-      p->launches += 2;
-    }
+    PROF(MCAG_PROF_SELECT_DOA);
+    int32_t *raw_idx = p->raw_idx.as<int32_t>() + o * T * S;
+    float *raw_prob = p->raw_prob.as<float>() + o * T * S;
+    OK(k_select_doa(energy, BT, D, P, S, raw_idx, raw_prob, st));
+    carry_cells_kernel<<<(B * S + 127) / 128, 128, 0, st>>>(raw_idx, raw_prob, active, B, T, S, p->cell_state.as<int32_t>() + o * S,
+                                                            p->prob_state.as<float>() + o * S, p->cells.as<int32_t>() + o * T * S,
+                                                            p->prob.as<float>() + o * T * S);
+    MCAG_CHECK_LAUNCH();
+    p->launches += 2;
     return MCAG_OK;
   };
   auto synth = [&](const float2 *src, int C) -> int {
     PROF(MCAG_PROF_ISTFT);
-    OK(k_istft(src, B, T, C, C, N, hop, p->win.as<float>(), p->tw.as<float2>(), p->tail[p->tail_cur].as<float>(),
-               p->tail[p->tail_cur ^ 1].as<float>(), p->out_dev.as<float>(), (long long)T * hop, st));
-    p->tail_cur ^= 1;
+    const long long ov = N - hop;
+    OK(k_istft(src, B, T, C, C, N, hop, win, tw, p->tail[p->tail_cur].as<float>() + o * C * ov, p->tail[p->tail_cur ^ 1].as<float>() + o * C * ov,
+               p->out_dev.as<float>() + o * C * T * hop, (long long)T * hop, st));
     p->launches++;
     return MCAG_OK;
   };
 
   if (kind == MCAG_KIND_SSL || kind == MCAG_KIND_SL) {
+    float *corr = p->corr.as<float>() + o * T * P * D;
     {
       PROF(MCAG_PROF_GCC_TAU);
-      OK(k_gcc_tau(spec, B, T, M, N, p->pair_fx.as<uint64_t>(), D, p->corr.as<float>(), st));
+      OK(k_gcc_tau(spec, B, T, M, N, p->pair_fx.as<uint64_t>(), D, corr, st));
       p->launches += (D <= 40) ? 1 : (D + 63) / 64;
     }
     {
       PROF(MCAG_PROF_ENERGY);
       const float a = p->cfg.energy_memory, b = 1.0f - p->cfg.energy_memory;   // float arithmetic as SteeringBeamforming.cpp:134,139
-      OK(k_pair_sum(p->corr.as<float>(), BT, P, D, b, p->esum.as<float>(), st));
-      OK(k_energy_scan(p->esum.as<float>(), B, T, D, a, active, p->energy_state.as<float>(), p->energy.as<float>(), st));
+      OK(k_pair_sum(corr, BT, P, D, b, esum, st));
+      OK(k_energy_scan(esum, B, T, D, a, active, energy_state, energy, st));
       p->launches += 2;
     }
     OK(select_and_carry());
     if (kind == MCAG_KIND_SSL) {
+      float2 *beams = p->beams.as<float2>() + o * T * Cs * KP;
       {
         PROF(MCAG_PROF_DS_SELECT);
-        OK(k_ds_select(spec, B, T, M, N, p->steer_tab.as<float2>(), p->cells.as<int32_t>(), S, p->Cs, p->beams.as<float2>(), st));
+        OK(k_ds_select(spec, B, T, M, N, p->steer_tab.as<float2>(), p->cells.as<int32_t>() + o * T * S, S, Cs, beams, st));
         p->launches++;
       }
-      OK(synth(p->beams.as<float2>(), p->Cs));
+      OK(synth(beams, Cs));
     }
   } else if (kind == MCAG_KIND_FREQGCC) {
+    float *corr = p->corr.as<float>() + o * T * D;
     {
       PROF(MCAG_PROF_GCC_TAU);
-      OK(k_gcc_tau(spec, B, T, 2, N, p->pair_fx.as<uint64_t>(), D, p->corr.as<float>(), st));
+      OK(k_gcc_tau(spec, B, T, 2, N, p->pair_fx.as<uint64_t>(), D, corr, st));
       p->launches += (D <= 40) ? 1 : (D + 63) / 64;
     }
     {
       PROF(MCAG_PROF_CURVE_SCAN);
-      OK(k_curve_scan_argmax(p->corr.as<float>(), B, T, D, 1.0f, p->cfg.corr_memory, active, p->curve_state.as<float>(),
-                             p->started.as<unsigned char>(), p->curves.as<float>(), p->cells.as<int32_t>(), st));
+      OK(k_curve_scan_argmax(corr, B, T, D, 1.0f, p->cfg.corr_memory, active, p->curve_state.as<float>() + o * D,
+                             p->started.as<unsigned char>() + o, p->curves.as<float>() + o * T * D, p->cells.as<int32_t>() + o * T, st));
       p->launches += 3;
     }
   } else if (kind == MCAG_KIND_DSFAN) {
     PROF(MCAG_PROF_DS_FAN);
-    OK(k_ds_fan(spec, B, T, M, N, p->steer_fx.as<uint64_t>(), D, p->beams.as<float2>(), st));
+    OK(k_ds_fan(spec, B, T, M, N, p->steer_fx.as<uint64_t>(), D, p->beams.as<float2>() + o * T * D * KP, st));
     p->launches++;
   } else if (kind == MCAG_KIND_SRP) {
     {
       PROF(MCAG_PROF_SRP);
-      OK(mcag_k_srp_tensor(spec, B, T, M, N, p->mic_fx.as<uint64_t>(), D, p->esum.as<float>(), st));
+      OK(mcag_k_srp_tensor(spec, B, T, M, N, p->mic_fx.as<uint64_t>(), D, esum, st));
       p->launches++;
     }
     {
       PROF(MCAG_PROF_ENERGY);
       // the pair sum enters the smoothing scaled by (1 - a), like every pair correlation (SteeringBeamforming.cpp:139)
-      OK(k_pair_sum(p->esum.as<float>(), BT, 1, D, 1.0f - p->cfg.energy_memory, p->energy.as<float>(), st));
-      OK(k_energy_scan(p->energy.as<float>(), B, T, D, p->cfg.energy_memory, active, p->energy_state.as<float>(), p->energy.as<float>(), st));
+      OK(k_pair_sum(esum, BT, 1, D, 1.0f - p->cfg.energy_memory, energy, st));
+      OK(k_energy_scan(energy, B, T, D, p->cfg.energy_memory, active, energy_state, energy, st));
       p->launches += 2;
     }
     OK(select_and_carry());
   } else if (kind == MCAG_KIND_MASK) {
-    const int nb = p->cfg.n_bands;
+    const int nb_ = p->cfg.n_bands;
     if (p->cfg.mask_method != 5) {   // NOTHING: pass-through (FastBinauralMasking.cpp:130-134)
+      float *stats = p->stats.as<float>() + o * T * nb_ * 6, *gains = p->gains.as<float>() + o * T * nb_ * 2;
       {
         PROF(MCAG_PROF_MASK_STATS);
-        OK(k_mask_stats(spec, BT, N, p->H2.as<float>(), nb, p->stats.as<float>(), st));
+        OK(k_mask_stats(spec, BT, N, p->H2.as<float>(), nb_, stats, st));
         p->launches++;
       }
       {
         PROF(MCAG_PROF_MASK_SCAN);
-        OK(k_mask_scan(p->stats.as<float>(), B, T, N, nb, p->cfg.mask_method, p->cfg.mask_alg, p->thr.as<float>(), p->Q.as<float>(),
-                       p->noise.as<float>(), (int)(p->frames_total > 2 ? 2 : p->frames_total), p->gains.as<float>(), p->dec.as<unsigned char>(),
-                       p->qtrace.as<float>(), st));
+        OK(k_mask_scan(stats, B, T, N, nb_, p->cfg.mask_method, p->cfg.mask_alg, p->thr.as<float>(), p->Q.as<float>() + o * nb_,
+                       p->noise.as<float>() + o * nb_, (int)(p->frames_total > 2 ? 2 : p->frames_total), gains,
+                       p->dec.as<unsigned char>() + o * T * nb_, p->qtrace.as<float>() + o * T * nb_, st));
         p->launches++;
       }
       {
         PROF(MCAG_PROF_MASK_APPLY);
-        OK(k_mask_apply(spec, BT, N, p->H.as<float>(), nb, p->gains.as<float>(), st));
+        OK(k_mask_apply(spec, BT, N, p->H.as<float>(), nb_, gains, st));
         p->launches++;
       }
     }
@@ -622,7 +637,7 @@ static int process_device_core(mcag_proc p, const float *d_new, long long pitch,
     CU(cudaMemcpy2DAsync(cur + p->fill, p->fifo_cap * 4, d_new, pitch * 4, (size_t)nsamples * 4, p->rows, cudaMemcpyDeviceToDevice, st));
     x = cur; xp = p->fifo_cap;
   }
-  if (T > 0) OK(run_frames(p, x, xp, T));
+  if (T > 0) { OK(run_frames(p, x, xp, T, 0, p->B)); if (p->Cs > 0) p->tail_cur ^= 1; }
   // carry the unconsumed samples
   const long long have = (long long)p->fill + nsamples, consumed = (long long)T * p->hop, left = have - consumed;
   if (left > 0) {
@@ -654,44 +669,90 @@ static int ensure_pinned(void **ptr, size_t *have, size_t need) {
   return MCAG_OK;
 }
 
+// out[r][off + i] = (float)in[r][i]: f64 / s16 input rows land in the FIFO in one pass
+template <class Tin>
+__global__ void convert_rows_kernel(const Tin *__restrict__ in, long long in_pitch, float *__restrict__ out, long long out_pitch, int n, int rows) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (i < n && r < rows) out[(long long)r * out_pitch + i] = (float)in[(long long)r * in_pitch + i];
+}
+
+constexpr int kMaxChunks = 8;
+
+// Host-buffer process call.  The streams of the handle are cut into up to kMaxChunks groups; group c+1 is copied host->device
+// on the copy-in stream while the kernels of group c run on the compute stream, and the audio of group c goes back on the
+// copy-out stream while group c+1 computes (PCIe is the bottleneck of the end-to-end path: 4 B per channel-sample in).
 template <class Tio>
 static int process_host(mcag_proc p, const Tio *const *in, const Tio *in_packed, long long in_pitch, int nsamples, Tio *const *out, Tio *out_packed,
                         long long out_pitch, int out_capacity, int *nsamples_out) {
   if (!p) return mcag_set_error(MCAG_ERR_INVALID, "null handle");
   if (nsamples < 0 || (!in && !in_packed && nsamples > 0)) return mcag_set_error(MCAG_ERR_INVALID, "bad input");
   CU(cudaSetDevice(p->cfg.device));
-  cudaStream_t st = p->stream;
-  const int rows = p->rows;
+  cudaStream_t st = p->stream, sin = p->copy_in, sout = p->copy_out;
+  const int rows = p->rows, B = p->B, M = p->M, Cs = p->Cs, Cout = p->Cout;
   const int T = frames_for(p, nsamples);
   if (T > p->Tmax) return mcag_set_error(MCAG_ERR_CAPACITY, "process: more frames than max_frames_per_call");
   if ((long long)p->fill + nsamples > p->fifo_cap) return mcag_set_error(MCAG_ERR_CAPACITY, "process: chunk larger than the input FIFO");
-  const bool want_audio = p->Cs > 0 && (out || out_packed);
+  const bool want_audio = Cs > 0 && (out || out_packed);
   if (want_audio && (long long)T * p->hop > out_capacity) return mcag_set_error(MCAG_ERR_CAPACITY, "process: output buffer too small");
+  constexpr bool is_f32 = Conv<Tio>::id == 0;
+  const int nout = T * p->hop;
 
-  // ---- host -> device: append to the FIFO (f32 directly; f64 / s16 through a device staging buffer + convert kernel)
+  const size_t in_bytes = (size_t)rows * nsamples * sizeof(Tio);
+  int nch = 1;
+  if (B >= 2 && in_bytes >= (size_t)8 << 20) nch = B < kMaxChunks ? B : kMaxChunks;
+
   float *cur = p->fifo[p->fifo_cur].as<float>();
-  if (nsamples > 0) {
-    if (Conv<Tio>::id == 0) {
-      if (in_packed) {
-        CU(cudaMemcpy2DAsync(cur + p->fill, p->fifo_cap * 4, in_packed, in_pitch * 4, (size_t)nsamples * 4, rows, cudaMemcpyHostToDevice, st));
-      } else {
-        for (int r = 0; r < rows; ++r) CU(cudaMemcpyAsync(cur + (long long)r * p->fifo_cap + p->fill, in[r], (size_t)nsamples * 4, cudaMemcpyHostToDevice, st));
-      }
+  if (!is_f32 && nsamples > 0 && p->stage_in.bytes < in_bytes) OK(p->stage_in.alloc(in_bytes));
+  if (want_audio && !is_f32 && nout > 0) OK(ensure_pinned(&p->pin_out, &p->pin_out_bytes, (size_t)B * Cs * nout * 4));
+
+  // ---- host -> device, one group of streams after the other on the copy-in stream
+  for (int c = 0; c < nch && nsamples > 0; ++c) {
+    const int r0 = (int)((long long)B * c / nch) * M, r1 = (int)((long long)B * (c + 1) / nch) * M;
+    if (is_f32) {
+      float *dst = cur + (long long)r0 * p->fifo_cap + p->fill;
+      if (in_packed) CU(cudaMemcpy2DAsync(dst, p->fifo_cap * 4, in_packed + (long long)r0 * in_pitch, in_pitch * 4, (size_t)nsamples * 4, r1 - r0, cudaMemcpyHostToDevice, sin));
+      else for (int r = r0; r < r1; ++r) CU(cudaMemcpyAsync(cur + (long long)r * p->fifo_cap + p->fill, in[r], (size_t)nsamples * 4, cudaMemcpyHostToDevice, sin));
     } else {
-      const size_t need = (size_t)rows * nsamples * sizeof(Tio);
-      if (p->stage_in.bytes < need) OK(p->stage_in.alloc(need));
-      if (p->stage_out.bytes < (size_t)rows * nsamples * 4) OK(p->stage_out.alloc((size_t)rows * nsamples * 4));
-      if (in_packed) CU(cudaMemcpy2DAsync(p->stage_in.p, (size_t)nsamples * sizeof(Tio), in_packed, in_pitch * sizeof(Tio), (size_t)nsamples * sizeof(Tio), rows, cudaMemcpyHostToDevice, st));
-      else for (int r = 0; r < rows; ++r) CU(cudaMemcpyAsync((char *)p->stage_in.p + (size_t)r * nsamples * sizeof(Tio), in[r], (size_t)nsamples * sizeof(Tio), cudaMemcpyHostToDevice, st));
-      const long long n = (long long)rows * nsamples;
-      if (Conv<Tio>::id == 1) f64_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p->stage_in.as<double>(), p->stage_out.as<float>(), n);
-      else s16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p->stage_in.as<int16_t>(), p->stage_out.as<float>(), n);
-      MCAG_CHECK_LAUNCH();
-      p->launches++;
-      CU(cudaMemcpy2DAsync(cur + p->fill, p->fifo_cap * 4, p->stage_out.p, (size_t)nsamples * 4, (size_t)nsamples * 4, rows, cudaMemcpyDeviceToDevice, st));
+      Tio *dst = p->stage_in.as<Tio>() + (long long)r0 * nsamples;
+      if (in_packed) CU(cudaMemcpy2DAsync(dst, (size_t)nsamples * sizeof(Tio), in_packed + (long long)r0 * in_pitch, in_pitch * sizeof(Tio), (size_t)nsamples * sizeof(Tio), r1 - r0, cudaMemcpyHostToDevice, sin));
+      else for (int r = r0; r < r1; ++r) CU(cudaMemcpyAsync(p->stage_in.as<Tio>() + (long long)r * nsamples, in[r], (size_t)nsamples * sizeof(Tio), cudaMemcpyHostToDevice, sin));
+    }
+    CU(cudaEventRecord(p->ev_in[c], sin));
+  }
+  // ---- kernels per group on the compute stream; audio of the group back on the copy-out stream
+  for (int c = 0; c < nch; ++c) {
+    const int b0 = (int)((long long)B * c / nch), b1 = (int)((long long)B * (c + 1) / nch);
+    if (nsamples > 0) {
+      CU(cudaStreamWaitEvent(st, p->ev_in[c], 0));
+      if (!is_f32) {
+        const int r0 = b0 * M, nr = (b1 - b0) * M;
+        dim3 grid((unsigned)((nsamples + 255) / 256), (unsigned)nr);
+        convert_rows_kernel<Tio><<<grid, 256, 0, st>>>(p->stage_in.as<Tio>() + (long long)r0 * nsamples, nsamples, cur + (long long)r0 * p->fifo_cap + p->fill,
+                                                       p->fifo_cap, nsamples, nr);
+        MCAG_CHECK_LAUNCH();
+        p->launches++;
+      }
+    }
+    if (T > 0) OK(run_frames(p, cur, p->fifo_cap, T, b0, b1 - b0));
+    if (want_audio && nout > 0) {
+      CU(cudaEventRecord(p->ev_done[c], st));
+      CU(cudaStreamWaitEvent(sout, p->ev_done[c], 0));
+      const float *src = p->out_dev.as<float>() + (long long)b0 * Cs * nout;
+      if (!is_f32) {
+        CU(cudaMemcpyAsync((float *)p->pin_out + (long long)b0 * Cs * nout, src, (size_t)(b1 - b0) * Cs * nout * 4, cudaMemcpyDeviceToHost, sout));
+      } else if (out_packed && Cs == Cout) {
+        CU(cudaMemcpy2DAsync(out_packed + (long long)b0 * Cout * out_pitch, out_pitch * 4, src, (size_t)nout * 4, (size_t)nout * 4, (size_t)(b1 - b0) * Cs, cudaMemcpyDeviceToHost, sout));
+      } else {
+        for (int b = b0; b < b1; ++b)
+          for (int ch = 0; ch < Cs; ++ch) {
+            Tio *dst = out_packed ? out_packed + ((long long)b * Cout + ch) * out_pitch : out[(long long)b * Cout + ch];
+            if (dst) CU(cudaMemcpyAsync(dst, p->out_dev.as<float>() + ((long long)b * Cs + ch) * nout, (size_t)nout * 4, cudaMemcpyDeviceToHost, sout));
+          }
+      }
     }
   }
-  if (T > 0) OK(run_frames(p, cur, p->fifo_cap, T));
+  if (T > 0 && Cs > 0) p->tail_cur ^= 1;
   const long long have = (long long)p->fill + nsamples, consumed = (long long)T * p->hop, left = have - consumed;
   if (left > 0 && consumed > 0) {
     float *nxt = p->fifo[p->fifo_cur ^ 1].as<float>();
@@ -701,31 +762,25 @@ static int process_host(mcag_proc p, const Tio *const *in, const Tio *in_packed,
   p->fill = (int)left;
   p->frames_last = T;
   p->frames_total += T;
-
-  // ---- device -> host: synthesised audio; channels >= Cs are zeros (BeamformingSeparationAndLocalisation.cpp:117-118)
-  const int nout = T * p->hop;
+  CU(cudaStreamSynchronize(st));
   if (want_audio && nout > 0) {
-    const int orow = p->B * p->Cs;
-    OK(ensure_pinned(&p->pin_out, &p->pin_out_bytes, (size_t)orow * nout * 4));
-    CU(cudaMemcpyAsync(p->pin_out, p->out_dev.p, (size_t)orow * nout * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(cudaStreamSynchronize(sout));
+    // channels >= Cs are zeros (BeamformingSeparationAndLocalisation.cpp:117-118); f64 / s16 are converted on the host
     const float *src = (const float *)p->pin_out;
-    for (int b = 0; b < p->B; ++b)
-      for (int c = 0; c < p->Cout; ++c) {
-        Tio *dst = out_packed ? out_packed + ((long long)b * p->Cout + c) * out_pitch : out[(long long)b * p->Cout + c];
+    for (int b = 0; b < B; ++b)
+      for (int ch = 0; ch < Cout; ++ch) {
+        Tio *dst = out_packed ? out_packed + ((long long)b * Cout + ch) * out_pitch : out[(long long)b * Cout + ch];
         if (!dst) continue;
-        if (c < p->Cs) {
-          const float *s = src + ((long long)b * p->Cs + c) * nout;
-          if (Conv<Tio>::id == 2) for (int i = 0; i < nout; ++i) { float v = nearbyintf(s[i]); dst[i] = (Tio)(v > 32767.f ? 32767.f : (v < -32768.f ? -32768.f : v)); }
-          else for (int i = 0; i < nout; ++i) dst[i] = (Tio)s[i];
-        } else {
+        if (ch >= Cs) {
           for (int i = 0; i < nout; ++i) dst[i] = (Tio)0;
+        } else if (!is_f32) {
+          const float *s_ = src + ((long long)b * Cs + ch) * nout;
+          if (Conv<Tio>::id == 2) for (int i = 0; i < nout; ++i) { float v = nearbyintf(s_[i]); dst[i] = (Tio)(v > 32767.f ? 32767.f : (v < -32768.f ? -32768.f : v)); }
+          else for (int i = 0; i < nout; ++i) dst[i] = (Tio)s_[i];
         }
       }
-  } else {
-    CU(cudaStreamSynchronize(st));
   }
-  if (nsamples_out) *nsamples_out = p->Cs > 0 ? nout : 0;
+  if (nsamples_out) *nsamples_out = Cs > 0 ? nout : 0;
   return MCAG_OK;
 }
 

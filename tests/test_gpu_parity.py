@@ -235,3 +235,28 @@ def test_srp_config4_parity(mb, orc):
     assert np.all(np.argmax(e, axis=1) == src)
     idx, _ = orc.select_doa(ref, 64 * 63 // 2, 1)
     assert np.array_equal(p.cells()[0], idx)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int16])
+def test_host_call_overlapped_stream_groups(mb, dtype):
+    """A host-buffer process call large enough to be cut into stream groups (copy / compute overlap inside the C ABI) must
+    give exactly what one-stream handles give, for every sample type of the reference's process() overloads, with state
+    (FIFO, overlap-add tail, energy smoothing) carried across two calls."""
+    fs, B = 16000, 12
+    xyz = scenes.linear_array([0, 0.07, 0.175, 0.21])
+    n1, n2 = 52000, 3000
+    x = np.stack([scenes.far_field_scene(xyz, fs, n1 + n2, scenes.azimuth_dirs([np.deg2rad(-60 + 10 * b)]), seed=scenes.stream_seed(b)) for b in range(B)])
+    x = np.round(x).astype(dtype)                                         # integers are exact in all three types
+    assert B * 4 * n1 * x.itemsize >= 8 << 20 or dtype == np.int16
+    big = mb.SourceSeparationAndLocalisation(fs, xyz, 1, usePowerFloor=False, n_streams=B, max_frames_per_call=256)
+    flat = x.reshape(B * 4, -1)
+    y1 = big.process(flat[:, :n1]); c1 = big.cells()
+    y2 = big.process(flat[:, n1:]); c2 = big.cells()
+    for b in range(B):
+        one = mb.SourceSeparationAndLocalisation(fs, xyz, 1, usePowerFloor=False, max_frames_per_call=256)
+        z1 = one.process(x[b][:, :n1]); d1 = one.cells()
+        z2 = one.process(x[b][:, n1:]); d2 = one.cells()
+        assert np.array_equal(c1[b], d1[0]) and np.array_equal(c2[b], d2[0])
+        assert np.array_equal(y1[4 * b:4 * b + 4], z1) and np.array_equal(y2[4 * b:4 * b + 4], z2)
+        one.close()
