@@ -160,6 +160,13 @@ const char *mcag_profile_name(int id);
 void *mcag_host_alloc(long long bytes);
 void mcag_host_free(void *ptr);
 
+/* Device memory helpers so plain C / C++ hosts can drive the kernel-level entry points without linking the CUDA runtime
+ * themselves (used by the frame-level classes mca::Beamformer / mca::SteeringBeamforming in include/mcarray/). */
+void *mcag_dev_alloc(long long bytes);                   /* zero-initialised; NULL on failure */
+void mcag_dev_free(void *d_ptr);
+int mcag_dev_upload(void *d_dst, const void *h_src, long long bytes);     /* synchronous */
+int mcag_dev_download(void *h_dst, const void *d_src, long long bytes);   /* synchronous (after all prior work on the default stream) */
+
 /* ---- kernel-level entry points on DEVICE buffers (what the processors are made of; also used by the parity tests) ----
  * `stream` is a cudaStream_t (NULL = default stream).  Spectra rows have pitch N/2+2 complex bins. */
 int mcag_k_twiddle_count(int N);                        /* float2 entries of the FFT tables for frame size N */

@@ -472,6 +472,24 @@ void *mcag_host_alloc(long long bytes) {
 }
 void mcag_host_free(void *ptr) { if (ptr) cudaFreeHost(ptr); }
 
+void *mcag_dev_alloc(long long bytes) {
+  void *ptr = nullptr;
+  if (bytes <= 0) bytes = 16;
+  if (cudaMalloc(&ptr, (size_t)bytes) != cudaSuccess) { mcag_set_error(MCAG_ERR_NOMEM, "cudaMalloc failed (mcarray_b200 has no CPU fallback)"); return nullptr; }
+  cudaMemset(ptr, 0, (size_t)bytes);
+  return ptr;
+}
+void mcag_dev_free(void *d_ptr) { if (d_ptr) cudaFree(d_ptr); }
+int mcag_dev_upload(void *d_dst, const void *h_src, long long bytes) {
+  CU(cudaMemcpy(d_dst, h_src, (size_t)bytes, cudaMemcpyHostToDevice));
+  return MCAG_OK;
+}
+int mcag_dev_download(void *h_dst, const void *d_src, long long bytes) {
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(h_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToHost));
+  return MCAG_OK;
+}
+
 }  // extern "C"
 
 // ----------------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,110 @@
+"""The C++ host layer (include/mcarray/*.h over the C ABI) and the mcbeam tool.
+
+CPU part: the library exports every symbol include/mcarray_b200.h declares, the host-side C++ builds with plain g++, the
+restated testArrayDescription (test/test_mcarray.cpp:518-580) passes, and GPU entry points fail loudly without a device.
+GPU part (-m gpu): the C++ classes and the CLI reproduce the golden fixtures made from the reference's own code."""
+import os
+import re
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+TOOLS = os.path.join(ROOT, "tools", "build")
+
+
+@pytest.fixture(scope="module")
+def tools():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "mcarray_b200", "csrc"), "-j8", "-s"], check=True)
+    subprocess.run(["make", "-C", os.path.join(ROOT, "tools"), "-s"], check=True)
+    return TOOLS
+
+
+def test_library_exports_every_declared_symbol(tools):
+    hdr = open(os.path.join(ROOT, "include", "mcarray_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(mcag_\w+)\s*\(", hdr))
+    assert len(declared) > 40
+    nm = subprocess.run(["nm", "-D", "--defined-only", os.path.join(ROOT, "mcarray_b200", "libmcarray_b200.so")], check=True, capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (mcag_\w+)", nm))
+    assert declared <= exported, sorted(declared - exported)
+
+
+def test_cpp_array_description(tools):
+    r = subprocess.run([os.path.join(tools, "test_mcarray_api"), "array"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "testArrayDescription ok" in r.stdout
+
+
+def test_cpp_fails_loudly_without_gpu(tools):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    r = subprocess.run([os.path.join(tools, "test_mcarray_api"), "frame"], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+def write_wav16(path, x, fs):
+    x = np.ascontiguousarray(x.T.astype("<i2"))
+    with open(path, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 36 + x.nbytes) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, x.shape[1], fs, fs * 2 * x.shape[1], 2 * x.shape[1], 16))
+        f.write(b"data" + struct.pack("<I", x.nbytes) + x.tobytes())
+
+
+def read_wav16(path):
+    b = open(path, "rb").read()
+    assert b[:4] == b"RIFF" and b[8:12] == b"WAVE"
+    ch, fs, bits = struct.unpack("<H", b[22:24])[0], struct.unpack("<I", b[24:28])[0], struct.unpack("<H", b[34:36])[0]
+    n = struct.unpack("<I", b[40:44])[0]
+    assert bits == 16
+    return np.frombuffer(b[44:44 + n], dtype="<i2").reshape(-1, ch).T, fs
+
+
+@pytest.mark.gpu
+def test_cpp_frame_level_classes(tools):
+    r = subprocess.run([os.path.join(tools, "test_mcarray_api"), "frame"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_ssl_against_reference_golden(tools, tmp_path):
+    g = np.load(os.path.join(G, "ssl_mcbeam_48k.npz"))
+    x = g["x"].astype(np.float64)
+    M, n = x.shape
+    x.tofile(tmp_path / "in.f64")
+    xs = ",".join(repr(float(v)) for v in g["xyz"][:, 0])
+    r = subprocess.run([os.path.join(tools, "test_mcarray_api"), "ssl", str(tmp_path / "in.f64"), str(M), str(n), str(int(g["fs"])), xs, str(int(g["chunk"])),
+                        str(tmp_path / "res")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = np.loadtxt(tmp_path / "res.doa").reshape(-1, 3)
+    assert rows.shape[0] == g["doa_deg"].shape[0]
+    assert np.array_equal(rows[:, 0], g["doa_deg"][:, 0])                                  # DOA cells exact (degrees of the grid cell)
+    assert np.allclose(rows[:, 1], g["prob"][:, 0], rtol=1e-4, atol=1e-6 + 1e-4 * np.max(np.abs(g["prob"])))
+    assert np.allclose(rows[:, 2], g["power"], atol=1e-3)
+    out = np.fromfile(tmp_path / "res.out")
+    ref = g["out"][0]
+    assert out.shape == ref.shape
+    assert np.max(np.abs(out - ref)) <= 1e-6 + 1e-4 * np.max(np.abs(ref))
+
+
+@pytest.mark.gpu
+def test_mcbeam_cli_against_reference_golden(tools, tmp_path):
+    """mcbeam -i in.wav -o out.wav -d doa.txt on the reference CLI's own hard-coded array (mcabeamf.cpp:182)."""
+    g = np.load(os.path.join(G, "ssl_mcbeam_48k.npz"))
+    fs = int(g["fs"])
+    write_wav16(tmp_path / "in.wav", g["x"], fs)
+    r = subprocess.run([os.path.join(tools, "mcbeam"), "-i", str(tmp_path / "in.wav"), "-o", str(tmp_path / "out.wav"), "-d", str(tmp_path / "doa.txt"), "-b", "8"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = [ln for ln in open(tmp_path / "doa.txt").read().split("\n") if ln]
+    m = [re.match(r"\[DOA: (\S+), p=(\S+), P=(\S+)\] $", ln) for ln in lines]           # line format of mcabeamf.cpp:66-70
+    assert all(m) and len(m) == g["doa_deg"].shape[0]
+    doa = np.array([float(k.group(1)) for k in m]); power = np.array([float(k.group(3)) for k in m])
+    assert np.allclose(doa, g["doa_deg"][:, 0], atol=1e-4)                                 # 6 significant digits of operator<<
+    assert np.allclose(power, g["power"] - 20 * np.log10(32768.0), atol=1e-2)              # the WAV reader normalises int16 by 2^-15
+    y, fs_out = read_wav16(tmp_path / "out.wav")
+    assert fs_out == fs and y.shape == g["out"].shape                                      # mono output: channel 0 only (:114-119)
+    assert np.max(np.abs(y[0] - g["out"][0])) <= 0.5 + 1e-4 * np.max(np.abs(g["out"]))
