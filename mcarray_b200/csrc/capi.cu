@@ -928,10 +928,5 @@ int mcag_k_ds_fan(const void *d_spec, int B, int T, int M, int N, const uint64_t
 int mcag_k_srp_channel(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_mic_fx, int D, float *d_srp, void *stream) {
   return k_srp_channel((const float2 *)d_spec, B, T, M, N, d_mic_fx, D, d_srp, (cudaStream_t)stream);
 }
-#ifndef MCAG_HAVE_SRP_TENSOR
-int mcag_k_srp_tensor(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_mic_fx, int D, float *d_srp, void *stream) {
-  return k_srp_channel((const float2 *)d_spec, B, T, M, N, d_mic_fx, D, d_srp, (cudaStream_t)stream);
-}
-#endif
 
 }  // extern "C"

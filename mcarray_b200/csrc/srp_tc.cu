@@ -1,0 +1,414 @@
+// K3 srp_contract on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
+//
+// Channel form of the SRP-PHAT pair sum of SteeringBeamforming::computeCorrelations (SteeringBeamforming.cpp:104-130,
+// SURVEY.md §8a row A4):   srp[t][d] = 1/2 sum_k ( |Y_k[t][d]|^2 - nz_k[t] ),   Y_k[t][d] = sum_m U_m[t][k] a_m[d][k],
+// U = X/|X| (PHAT whitening), a_m[d][k] = exp(-j 2 pi k tau_m(d) / N).  Per bin k this is a complex [T x M] . [M x D]
+// contraction, run as a real GEMM with the real / imaginary parts stacked along K (2M) and along N (2 x directions):
+//
+//     D[t][n] += A[t][c] * B[n][c]        A = frames (UMMA M = 128 rows, K-major)      c = 2m + {re, im}
+//                                          B = steering (UMMA N = 256 rows, K-major)    n = d (Re rows 0..127), 128 + d (Im rows)
+//     B[d][2m] = Re a, B[d][2m+1] = -Im a;   B[128+d][2m] = Im a, B[128+d][2m+1] = Re a
+//
+// fp32 accuracy comes from the 3xTF32 split: x = hi + lo with hi = the TF32 the tensor core would read (low 13 mantissa bits
+// cleared) and lo = x - hi (exact); D += A_hi B_hi + A_lo B_hi + A_hi B_lo (the dropped lo*lo term is ~2^-22 relative).
+//
+// Data flow per CTA (persistent over work items = frame tile x direction tile x bin range, 1 CTA per SM):
+//   warp 0      TMA producer: the frames operand comes from a bin-major, pre-whitened, pre-split copy of the spectra
+//               (srp_prepare_kernel) as 128B-swizzled [128 x 32] fp32 boxes, hi and lo, per 32-float K chunk
+//   warp 1      MMA issuer: one thread issues 12 tcgen05.mma.kind::tf32 (M128 N256 K8) per K chunk into one of two
+//               256-column TMEM accumulators, commits the smem stage back to the producers and the accumulator to the epilogue
+//   warps 4-11  steering generators: the B operand is never loaded - each thread keeps the 32-bit fixed-point phase
+//               increments of its (direction, microphone) elements in registers, evaluates sin/cos of k*increment for the
+//               current bin and writes the hi / lo tiles straight into shared memory in the canonical swizzled layout
+//   warps 12-19 epilogue: tcgen05.ld the finished accumulator, square, accumulate over the bins of the work item in registers
+//               (|Y|^2 is not linear, so it cannot stay in TMEM), and store the partial energy map at the end of the item
+// A second small kernel adds the partial maps in a fixed order (deterministic) and applies the -nz/2 term.
+#include "common.cuh"
+#include "kernels.h"
+
+#include <cuda.h>
+
+namespace mcag {
+
+constexpr int TC_BM = 128;        // frames per tile (UMMA M)
+constexpr int TC_BD = 128;        // directions per tile (UMMA N = 2 * TC_BD)
+constexpr int TC_KC = 32;         // floats per K chunk = one 128-byte swizzle row
+constexpr int TC_STAGES = 2;
+constexpr int TC_GEN_THREADS = 256, TC_EPI_THREADS = 256;
+constexpr int TC_THREADS = 128 + TC_GEN_THREADS + TC_EPI_THREADS;
+constexpr int TC_A_BYTES = TC_BM * TC_KC * 4;          // 16 KB
+constexpr int TC_B_BYTES = 2 * TC_BD * TC_KC * 4;      // 32 KB
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 96 KB
+constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded spin: a pipeline bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (spin > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N = 256, M = 128
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// ---- pre-pass: whiten, split, transpose to bin-major --------------------------------------------------------------------
+// spec [BT][M][KP] float2  ->  U_hi / U_lo [K][BTpad][2M] fp32 (rows t >= BT stay zero), nzsum[t] = sum_k #(non-zero channels)
+__global__ void __launch_bounds__(256) srp_prepare_kernel(const float2 *__restrict__ spec, long long BT, long long BTpad, int M, int N,
+                                                           float *__restrict__ Uhi, float *__restrict__ Ulo, float *__restrict__ nzsum) {
+  __shared__ float2 s_t[32][65];   // [bin in chunk][mic], M <= 64
+  __shared__ float s_nz[8];
+  const int KP = spec_pitch(N), K = N / 2 + 1;
+  const long long t = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float nz = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    for (int m = warp; m < M; m += 8) {   // coalesced along k
+      const int k = k0 + lane;
+      float2 u = make_float2(0.f, 0.f);
+      if (k < K) {
+        u = whiten(spec[(t * M + m) * KP + k]);
+        nz += (u.x != 0.f || u.y != 0.f) ? 1.f : 0.f;
+      }
+      s_t[lane][m] = u;
+    }
+    __syncthreads();
+    for (int i = tid; i < 32 * M; i += 256) {   // coalesced along m (8 bytes per mic)
+      const int kk = i / M, m = i - kk * M, k = k0 + kk;
+      if (k < K) {
+        const float2 u = s_t[kk][m];
+        const float2 h = make_float2(tf32_hi(u.x), tf32_hi(u.y));
+        const long long o = ((long long)k * BTpad + t) * (2 * M) + 2 * m;
+        *reinterpret_cast<float2 *>(Uhi + o) = h;
+        *reinterpret_cast<float2 *>(Ulo + o) = make_float2(u.x - h.x, u.y - h.y);
+      }
+    }
+    __syncthreads();
+  }
+  nz = warp_sum(nz);
+  if (lane == 0) s_nz[warp] = nz;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += s_nz[w];
+    nzsum[t] = s;
+  }
+}
+
+// ---- main kernel -----------------------------------------------------------------------------------------------------------
+struct TcParams {
+  long long BT;          // frames (all streams)
+  int D, M, K;           // directions, microphones, one-sided bins
+  int n_tt, n_dt, n_ks;  // frame tiles, direction tiles, bin ranges
+  int bins_per_range;
+  const uint64_t *mic_fx;   // [D][M] 0.64 fixed-point turns per bin
+  float *partial;           // [n_ks][BT][D]
+};
+
+template <int NKC>   // K chunks per bin = 2M / 32 = M / 16
+__global__ void __launch_bounds__(TC_THREADS, 1) srp_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                                                                const TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t *full_a = bars, *full_b = bars + TC_STAGES, *empty = bars + 2 * TC_STAGES, *tmem_full = bars + 3 * TC_STAGES,
+           *tmem_empty = bars + 3 * TC_STAGES + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * TC_STAGES + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_a[s], 1); mbar_init(&full_b[s], TC_GEN_THREADS); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], TC_EPI_THREADS); }
+  }
+  if (warp == 1) {   // TMEM: all 512 columns (two 256-column accumulators); 1 CTA per SM
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_items = p.n_tt * p.n_dt * p.n_ks;
+
+  if (warp == 0) {
+    // ===== TMA producer (frames operand) =====
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
+      int stage = 0; uint32_t phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int ks = item / (p.n_tt * p.n_dt), tt = (item / p.n_dt) % p.n_tt;
+        const int k_begin = ks * p.bins_per_range, k_end = min(p.K, k_begin + p.bins_per_range);
+        for (int k = k_begin; k < k_end; ++k)
+          for (int cc = 0; cc < NKC; ++cc) {
+            mbar_wait_bounded(&empty[stage], phase ^ 1);
+            unsigned char *st = smem + stage * TC_STAGE_BYTES;
+            mbar_expect_tx(&full_a[stage], 2 * TC_A_BYTES);
+            tma_load_3d(st, &map_hi, &full_a[stage], cc * TC_KC, tt * TC_BM, k);
+            tma_load_3d(st + TC_A_BYTES, &map_lo, &full_a[stage], cc * TC_KC, tt * TC_BM, k);
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int ks = item / (p.n_tt * p.n_dt);
+        const int k_begin = ks * p.bins_per_range, k_end = min(p.K, k_begin + p.bins_per_range);
+        for (int k = k_begin; k < k_end; ++k) {
+          mbar_wait_bounded(&tmem_empty[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+          for (int cc = 0; cc < NKC; ++cc) {
+            mbar_wait_bounded(&full_a[stage], phase);
+            mbar_wait_bounded(&full_b[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES);
+            const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + TC_A_BYTES);
+            const uint64_t b_hi = umma_desc_sw128(sa + 2 * TC_A_BYTES), b_lo = umma_desc_sw128(sa + 2 * TC_A_BYTES + TC_B_BYTES);
+#pragma unroll
+            for (int j = 0; j < TC_KC / 8; ++j) {   // K = 8 per instruction: 32 bytes along the swizzled row -> +2 in the address field
+              umma_tf32(d_tmem, a_hi + 2 * j, b_hi + 2 * j, TC_IDESC, (cc | j) != 0);
+              umma_tf32(d_tmem, a_lo + 2 * j, b_hi + 2 * j, TC_IDESC, 1);
+              umma_tf32(d_tmem, a_hi + 2 * j, b_lo + 2 * j, TC_IDESC, 1);
+            }
+            umma_commit(&empty[stage]);   // frees the smem stage once these MMAs have read it
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tmem_full[acc]);    // accumulator of bin k complete
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 4 + TC_GEN_THREADS / 32) {
+    // ===== steering generators (B operand) =====
+    const int g = tid - 128;
+    const int dl = g & (TC_BD - 1), grp = g >> 7;   // direction within the tile; which half of the microphone pairs of a chunk
+    int stage = 0; uint32_t phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int ks = item / (p.n_tt * p.n_dt), dt = item % p.n_dt;
+      const int k_begin = ks * p.bins_per_range, k_end = min(p.K, k_begin + p.bins_per_range);
+      const int d = min(dt * TC_BD + dl, p.D - 1);
+      // 32-bit fixed-point turns per bin of this thread's (direction, microphone) elements; k * fx wraps exactly mod 1 turn
+      uint32_t fx[NKC * 8];
+#pragma unroll
+      for (int cc = 0; cc < NKC; ++cc)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int m = cc * 16 + grp * 8 + u;
+          const uint64_t f = p.mic_fx[(size_t)d * p.M + m];
+          fx[cc * 8 + u] = (uint32_t)((f + 0x80000000ull) >> 32);
+        }
+      const uint32_t row_re = (uint32_t)dl * 128u, row_im = (uint32_t)(TC_BD + dl) * 128u;
+      const uint32_t sw = (uint32_t)(dl & 7);   // (128 + dl) & 7 == dl & 7
+      for (int k = k_begin; k < k_end; ++k)
+#pragma unroll
+        for (int cc = 0; cc < NKC; ++cc) {
+          float c[8], s[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int32_t ph = (int32_t)(fx[cc * 8 + u] * (uint32_t)k);                       // signed turns * 2^32
+            __sincosf((float)ph * 1.4629180792671596e-09f, &s[u], &c[u]);                     // 2 pi / 2^32
+          }
+          mbar_wait_bounded(&empty[stage], phase ^ 1);
+          unsigned char *bh = smem + stage * TC_STAGE_BYTES + 2 * TC_A_BYTES, *bl = bh + TC_B_BYTES;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {   // two microphones = one 16-byte chunk of the Re row and of the Im row
+            const float ch0 = tf32_hi(c[2 * u]), sh0 = tf32_hi(s[2 * u]), ch1 = tf32_hi(c[2 * u + 1]), sh1 = tf32_hi(s[2 * u + 1]);
+            const float cl0 = c[2 * u] - ch0, sl0 = s[2 * u] - sh0, cl1 = c[2 * u + 1] - ch1, sl1 = s[2 * u + 1] - sh1;
+            const uint32_t q = ((uint32_t)(grp * 4 + u) ^ sw) << 4;   // 16-byte chunk, 128B swizzle
+            *reinterpret_cast<float4 *>(bh + row_re + q) = make_float4(ch0, -sh0, ch1, -sh1);
+            *reinterpret_cast<float4 *>(bh + row_im + q) = make_float4(sh0, ch0, sh1, ch1);
+            *reinterpret_cast<float4 *>(bl + row_re + q) = make_float4(cl0, -sl0, cl1, -sl1);
+            *reinterpret_cast<float4 *>(bl + row_im + q) = make_float4(sl0, cl0, sl1, cl1);
+          }
+          fence_async_smem();            // generic-proxy stores -> visible to the tensor core (async proxy)
+          mbar_arrive(&full_b[stage]);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+    }
+  } else if (warp >= 4 + TC_GEN_THREADS / 32) {
+    // ===== epilogue: TMEM -> registers, square, accumulate over bins =====
+    const int e = warp - (4 + TC_GEN_THREADS / 32);
+    const int quarter = warp & 3, half = e >> 2;   // TMEM lanes 32*quarter..+31 are the ones this warp may touch; which 64 directions
+    constexpr int HD = TC_BD / 2;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int ks = item / (p.n_tt * p.n_dt), tt = (item / p.n_dt) % p.n_tt, dt = item % p.n_dt;
+      const int k_begin = ks * p.bins_per_range, k_end = min(p.K, k_begin + p.bins_per_range);
+      float sum[HD];
+#pragma unroll
+      for (int i = 0; i < HD; ++i) sum[i] = 0.f;
+      for (int k = k_begin; k < k_end; ++k) {
+        mbar_wait_bounded(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + half * HD);
+#pragma unroll
+        for (int j = 0; j < HD / 16; ++j) {
+          float vr[16], vi[16];
+          tmem_ld16(taddr + j * 16, vr);              // Re Y of 16 directions
+          tmem_ld16(taddr + TC_BD + j * 16, vi);      // Im Y of the same directions
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sum[j * 16 + i] = fmaf(vi[i], vi[i], fmaf(vr[i], vr[i], sum[j * 16 + i]));
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      const long long t = (long long)tt * TC_BM + quarter * 32 + lane;
+      if (t < p.BT) {
+        const int d0 = dt * TC_BD + half * HD;
+        float *dst = p.partial + (((long long)ks * p.BT + t) * p.D) + d0;
+        const int nd = min(HD, p.D - d0);
+        if (nd == HD && (p.D & 3) == 0) {
+#pragma unroll
+          for (int i = 0; i < HD; i += 4) *reinterpret_cast<float4 *>(dst + i) = make_float4(sum[i], sum[i + 1], sum[i + 2], sum[i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < HD; ++i) if (i < nd) dst[i] = sum[i];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+// srp[t][d] = 1/2 ( sum_s partial[s][t][d] - nzsum[t] ), partial maps added in index order
+__global__ void srp_reduce_kernel(const float *__restrict__ partial, int n_part, long long BT, int D, const float *__restrict__ nzsum,
+                                  float *__restrict__ srp) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BT * D) return;
+  float acc = 0.f;
+  for (int s = 0; s < n_part; ++s) acc += partial[(long long)s * BT * D + i];
+  srp[i] = 0.5f * (acc - nzsum[i / D]);
+}
+
+static int encode_map(CUtensorMap *map, const float *base, long long BTpad, int M, int K) {
+  cuuint64_t dims[3] = {(cuuint64_t)(2 * M), (cuuint64_t)BTpad, (cuuint64_t)K};
+  cuuint64_t strides[2] = {(cuuint64_t)(2 * M) * 4, (cuuint64_t)BTpad * (2 * M) * 4};
+  cuuint32_t box[3] = {TC_KC, TC_BM, 1}, estr[3] = {1, 1, 1};
+  CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return mcag_set_error(2, "cuTensorMapEncodeTiled failed");
+  return 0;
+}
+
+template <int NKC> static void launch_tc(int grid, cudaStream_t st, const CUtensorMap &hi, const CUtensorMap &lo, const TcParams &p) {
+  auto kern = srp_tc_kernel<NKC>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+  kern<<<grid, TC_THREADS, TC_SMEM, st>>>(hi, lo, p);
+}
+
+// Supported shapes: M in {16, 32, 48, 64}; anything else runs the CUDA-core tile kernel (still on the GPU).
+int k_srp_tensor(const float2 *spec, int B, int T, int M, int N, const uint64_t *mic_fx, int D, float *srp, cudaStream_t st) {
+  if (B <= 0 || T <= 0) return 0;
+  if (M % 16 != 0 || M < 16 || M > 64) return k_srp_channel(spec, B, T, M, N, mic_fx, D, srp, st);
+  const long long BT = (long long)B * T, BTpad = (BT + TC_BM - 1) / TC_BM * TC_BM;
+  const int K = N / 2 + 1;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  TcParams p;
+  p.BT = BT; p.D = D; p.M = M; p.K = K; p.mic_fx = mic_fx;
+  p.n_tt = (int)(BTpad / TC_BM); p.n_dt = (D + TC_BD - 1) / TC_BD;
+  // bin ranges: enough work items for ~4 waves of persistent CTAs, at least 16 bins each
+  long long tiles = (long long)p.n_tt * p.n_dt;
+  int n_ks = (int)((4LL * sms + tiles - 1) / tiles);
+  if (n_ks > K / 16) n_ks = K / 16;
+  if (n_ks < 1) n_ks = 1;
+  p.bins_per_range = (K + n_ks - 1) / n_ks;
+  p.n_ks = (K + p.bins_per_range - 1) / p.bins_per_range;
+  const size_t u_bytes = (size_t)K * BTpad * 2 * M * sizeof(float), part_bytes = (size_t)p.n_ks * BT * D * sizeof(float);
+  float *Uhi = nullptr, *Ulo = nullptr, *partial = nullptr, *nzsum = nullptr;
+  if (cudaMallocAsync(&Uhi, u_bytes, st) != cudaSuccess || cudaMallocAsync(&Ulo, u_bytes, st) != cudaSuccess ||
+      cudaMallocAsync(&partial, part_bytes, st) != cudaSuccess || cudaMallocAsync(&nzsum, (size_t)BT * sizeof(float), st) != cudaSuccess)
+    return mcag_set_cuda_error(cudaGetLastError());
+  p.partial = partial;
+  if (BTpad != BT) { cudaMemsetAsync(Uhi, 0, u_bytes, st); cudaMemsetAsync(Ulo, 0, u_bytes, st); }
+  srp_prepare_kernel<<<(unsigned)BT, 256, 0, st>>>(spec, BT, BTpad, M, N, Uhi, Ulo, nzsum);
+  MCAG_CHECK_LAUNCH();
+  CUtensorMap map_hi, map_lo;
+  int rc = encode_map(&map_hi, Uhi, BTpad, M, K);
+  if (!rc) rc = encode_map(&map_lo, Ulo, BTpad, M, K);
+  if (!rc) {
+    const long long items = (long long)p.n_tt * p.n_dt * p.n_ks;
+    const int grid = (int)(items < sms ? items : sms);
+    switch (M / 16) {
+      case 1: launch_tc<1>(grid, st, map_hi, map_lo, p); break;
+      case 2: launch_tc<2>(grid, st, map_hi, map_lo, p); break;
+      case 3: launch_tc<3>(grid, st, map_hi, map_lo, p); break;
+      default: launch_tc<4>(grid, st, map_hi, map_lo, p); break;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = mcag_set_cuda_error(e);
+  }
+  if (!rc) {
+    const long long n = BT * D;
+    srp_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, p.n_ks, BT, D, nzsum, srp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = mcag_set_cuda_error(e);
+  }
+  cudaFreeAsync(Uhi, st); cudaFreeAsync(Ulo, st); cudaFreeAsync(partial, st); cudaFreeAsync(nzsum, st);
+  return rc;
+}
+
+}  // namespace mcag
+
+extern "C" int mcag_k_srp_tensor(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_mic_fx, int D, float *d_srp, void *stream) {
+  return mcag::k_srp_tensor((const float2 *)d_spec, B, T, M, N, d_mic_fx, D, d_srp, (cudaStream_t)stream);
+}

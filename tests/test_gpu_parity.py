@@ -260,3 +260,33 @@ def test_host_call_overlapped_stream_groups(mb, dtype):
         assert np.array_equal(c1[b], d1[0]) and np.array_equal(c2[b], d2[0])
         assert np.array_equal(y1[4 * b:4 * b + 4], z1) and np.array_equal(y2[4 * b:4 * b + 4], z2)
         one.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,BT,D,N", [(64, 200, 300, 512), (32, 130, 257, 256), (16, 5, 64, 1024), (48, 128, 128, 512)])
+def test_srp_tensor_kernel_vs_cuda_core_kernel(mb, M, BT, D, N):
+    """K3 on tcgen05 (3xTF32, TMA-fed frames operand, generated steering operand) against the CUDA-core channel-form kernel on
+    the same random spectra: partial frame / direction tiles, every supported microphone count, zero bins included."""
+    import ctypes as C
+    import torch
+    from mcarray_b200 import capi
+    lib = capi.lib()
+    g = torch.Generator(device="cuda").manual_seed(M * 1000 + BT)
+    KP = N // 2 + 2
+    spec = torch.randn(BT, M, KP, 2, device="cuda", generator=g) * 100
+    spec[:, :, N // 2 + 1:] = 0
+    spec[:, :, 0, 1] = 0; spec[:, :, N // 2, 1] = 0
+    spec[3 % BT, 1, 7] = 0                                   # a silent bin: the nz term must follow it
+    rng = np.random.default_rng(D)
+    turns = np.ascontiguousarray(rng.uniform(-40, 40, size=(D, M)) / N)       # -tau/N turns per bin, |tau| up to 40 samples
+    fx = torch.empty(D * M, dtype=torch.int64, device="cuda")
+    capi.check(lib.mcag_k_phase_fx(capi.dp(turns), C.c_longlong(D * M), capi.vp(fx), None))
+    out_c = torch.empty(BT, D, device="cuda"); out_t = torch.empty(BT, D, device="cuda")
+    torch.cuda.synchronize()
+    capi.check(lib.mcag_k_srp_channel(capi.vp(spec), 1, BT, M, N, capi.vp(fx), D, capi.vp(out_c), None))
+    capi.check(lib.mcag_k_srp_tensor(capi.vp(spec), 1, BT, M, N, capi.vp(fx), D, capi.vp(out_t), None))
+    torch.cuda.synchronize()
+    a, b = out_t.cpu().numpy(), out_c.cpu().numpy()
+    assert np.isfinite(a).all()
+    scale = np.max(np.abs(b), axis=1, keepdims=True)
+    assert np.max(np.abs(a - b) / (ATOL + RTOL * scale)) <= 1.0, np.max(np.abs(a - b) / scale)
