@@ -149,7 +149,58 @@ class Cfg5(Workload):
         return res
 
 
-WORKLOADS = {"cfg2": Cfg2, "cfg5": Cfg5}
+class Cfg4(Workload):
+    """64-mic planar array SRP-PHAT over a 3600-direction azimuth x elevation grid (BASELINE.json configs[3]); tensor-core contraction."""
+    name = "cfg4: 64-mic 8x8 planar array 0.04 m pitch, SRP-PHAT over 120 az x 30 el = 3600 directions, 48 kHz, N=1024, hop=512"
+    fs, N, hop, M, D = 48000, 1024, 512, 64, 3600
+    B_default, T_default = 4, 256
+    bound = "tensor"
+    cpu_frames, cpu_streams = (4, 16), 1                            # ~0.95 GFLOP (x2 in float64 complex) per frame on the CPU
+
+    def xyz(self):
+        from mcarray_b200 import scenes
+        return scenes.planar_array(8, 8, 0.04)
+
+    def dirs(self):
+        from mcarray_b200 import scenes
+        az = np.linspace(-np.pi, np.pi, 120, endpoint=False); el = np.linspace(0.05, 1.45, 30)
+        return scenes.az_el_dirs(az[:, None], el[None, :])
+
+    def scene(self, stream_id, n):
+        from mcarray_b200 import scenes
+        d = self.dirs()
+        src = (stream_id * 997 + 57 * 30 + 11) % len(d)
+        return scenes.far_field_scene(self.xyz(), self.fs, n, d[src:src + 1], seed=scenes.stream_seed(stream_id))
+
+    def make(self, mb, B, T):
+        return mb.SrpPhat(self.fs, self.xyz(), self.N, self.dirs(), numOfSources=1, n_streams=B, max_frames_per_call=T)
+
+    def result_bytes(self, p, B, T):
+        return B * T * 4
+
+    def fetch_result(self, p):
+        return p.cells()
+
+    def kernel_bytes_per_frame(self):
+        M, hop, K, D = self.M, self.hop, self.N // 2 + 1, self.D
+        return {"stft": 4 * M * hop + 8 * M * K, "srp": 8 * M * K + 4 * D, "energy": 8 * D, "select_doa": 4 * D + 8}
+
+    def kernel_flops_per_frame(self):
+        return {"srp": 8 * self.D * self.M * (self.N // 2 + 1)}     # complex MAC = 8 real flops (SURVEY.md §8d)
+
+    def pipeline_bytes_per_frame(self):
+        return 4 * self.M * self.hop + 4 * self.D + 8               # SURVEY.md §8d: 145 480 B
+
+    def cpu_run(self, orc, x64, n_threads):
+        mt = orc.mic_tau(self.xyz(), self.fs, self.dirs())
+        out = []
+        for x in x64:                                               # threads are inside orc.srp_channel (over directions)
+            S = orc.stft(x, self.N, self.hop)
+            out.append(np.argmax(orc.srp_channel(S, self.N, mt, n_threads=n_threads), axis=1))
+        return out
+
+
+WORKLOADS = {"cfg2": Cfg2, "cfg4": Cfg4, "cfg5": Cfg5}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -209,9 +260,9 @@ def run_cpu(wl, args, rank, world, as_reference_arm):
     import orc
     cores = os.cpu_count() or 1
     if not args.cpu_frames:
-        args.cpu_frames = 128 if as_reference_arm else 512
+        args.cpu_frames = getattr(wl, "cpu_frames", (128, 512))[0 if as_reference_arm else 1]
     n = wl.N + (args.cpu_frames - 1) * wl.hop
-    Bc = max(cores, 1) * args.cpu_streams_per_core
+    Bc = getattr(wl, "cpu_streams", max(cores, 1) * args.cpu_streams_per_core)
     x = np.stack([wl.scene(10_000 + b % 4, n) for b in range(min(Bc, 4))])
     x64 = np.ascontiguousarray(np.concatenate([x] * ((Bc + len(x) - 1) // len(x)))[:Bc])
     units = Bc * wl.M * args.cpu_frames * wl.hop
@@ -381,7 +432,20 @@ def main():
     per_launch_ms = dom_ms / dom_n
     bytes_per_launch = kb.get(dom, wl.pipeline_bytes_per_frame()) * B * T
     achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+    flops = getattr(wl, "kernel_flops_per_frame", lambda: {})().get(dom)
+    if getattr(wl, "bound", "hbm") == "tensor" and flops:
+        # 3xTF32: every algorithmic flop is issued three times on the TF32 pipe; TF32 dense peak = half the measured bf16 GEMM rate
+        issued = 3.0 * flops * B * T / (per_launch_ms * 1e-3) / 1e12
+        peak_tf32 = peaks["bf16_tflops"] / 2.0
+        roofline_t = {"bound": "tensor", "kernel": dom, "achieved": issued, "peak": peak_tf32, "unit": "TFLOP/s", "frac": issued / peak_tf32, "traffic": None,
+                      "peak_source": peaks["source"] + ": cuBLAS bf16 burst / 2 = dense TF32 rate", "algorithmic_flops_per_launch": flops * B * T,
+                      "algorithmic_tflops": flops * B * T / (per_launch_ms * 1e-3) / 1e12, "issue_factor": "3xTF32 (hi*hi + lo*hi + hi*lo)",
+                      "ms_per_launch": per_launch_ms, "kernel_share_of_step": dom_ms / tot,
+                      "hbm": {"algorithmic_bytes_per_launch": bytes_per_launch, "achieved_gbs": achieved, "frac": achieved / peaks["hbm_gbs"]},
+                      "kernels_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}}
+    else:
+        roofline_t = None
+    roofline = roofline_t or {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 "traffic": None, "peak_source": peaks["source"], "algorithmic_bytes_per_launch": bytes_per_launch, "ms_per_launch": per_launch_ms,
                 "kernel_share_of_step": dom_ms / tot,
                 "pipeline": {"algorithmic_bytes_per_frame": wl.pipeline_bytes_per_frame(),

@@ -180,7 +180,7 @@ struct mcag_proc_s {
   DevBuf pair_fx, corr, esum, energy, energy_state, raw_idx, raw_prob, cells, prob, cell_state, prob_state;
   DevBuf steer_fx, steer_tab, beams, tail[2], out_dev; int tail_cur = 0;
   DevBuf lags, curves, curve_state, started;
-  DevBuf mic_fx;
+  DevBuf mic_fx, srp_ws;
   DevBuf H, H2, thr, stats, gains, Q, noise, dec, qtrace;
   void *pin_in = nullptr, *pin_out = nullptr; size_t pin_in_bytes = 0, pin_out_bytes = 0;
   std::vector<double> h_window;
@@ -360,6 +360,8 @@ int mcag_create(const mcag_config *cfg, mcag_proc *out) {
     std::vector<double> turns(D * M);   // device layout [D][M], exp(-j 2 pi k tau_m / N)
     for (size_t m = 0; m < M; ++m) for (size_t d = 0; d < D; ++d) turns[d * M + m] = -cfg->mic_tau[m * D + d] / (double)N;
     if ((rc = upload_fx(p->mic_fx, turns.data(), turns.size(), st))) return fail(rc);
+    if (k_srp_tensor_supported(p->M))   // scratch of the tcgen05 contraction: bin-major whitened spectra (hi / lo) + partial energy maps
+      if ((rc = p->srp_ws.alloc(k_srp_tensor_workspace_bytes((long long)B * T, p->M, N, p->D)))) return fail(rc);
   }
   if (p->Cs > 0) {
     if ((rc = p->beams.alloc(sizeof(float2) * B * T * (kind == MCAG_KIND_MASK ? 2 : p->Cs) * KP))) return fail(rc);
@@ -395,7 +397,7 @@ void mcag_destroy(mcag_proc p) {
   DevBuf *all[] = {&p->fifo[0], &p->fifo[1], &p->stage_in, &p->stage_out, &p->win, &p->tw, &p->spec, &p->chan_pow, &p->chan_raw, &p->power_db,
                    &p->active, &p->gate, &p->pair_fx, &p->corr, &p->esum, &p->energy, &p->energy_state, &p->raw_idx, &p->raw_prob, &p->cells,
                    &p->prob, &p->cell_state, &p->prob_state, &p->steer_fx, &p->steer_tab, &p->beams, &p->tail[0], &p->tail[1], &p->out_dev,
-                   &p->lags, &p->curves, &p->curve_state, &p->started, &p->mic_fx, &p->H, &p->H2, &p->thr, &p->stats, &p->gains, &p->Q,
+                   &p->lags, &p->curves, &p->curve_state, &p->started, &p->mic_fx, &p->srp_ws, &p->H, &p->H2, &p->thr, &p->stats, &p->gains, &p->Q,
                    &p->noise, &p->dec, &p->qtrace};
   for (DevBuf *b : all) b->release();
   for (auto &r : p->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -597,8 +599,8 @@ static int run_frames(mcag_proc p, const float *x_all, long long pitch, int T, i
   } else if (kind == MCAG_KIND_SRP) {
     {
       PROF(MCAG_PROF_SRP);
-      OK(mcag_k_srp_tensor(spec, B, T, M, N, p->mic_fx.as<uint64_t>(), D, esum, st));
-      p->launches++;
+      OK(k_srp_tensor_ws(spec, B, T, M, N, p->mic_fx.as<uint64_t>(), D, esum, p->srp_ws.p, p->srp_ws.bytes, st));
+      p->launches += 3;   // prepare (whiten / split / transpose), tcgen05 contraction, partial-map reduction
     }
     {
       PROF(MCAG_PROF_ENERGY);

@@ -35,6 +35,13 @@ int k_ds_fan(const float2 *spec, int B, int T, int M, int N, const uint64_t *ste
 // srp.cu
 int k_srp_channel(const float2 *spec, int B, int T, int M, int N, const uint64_t *mic_fx, int D, float *srp, cudaStream_t st);
 
+// srp_tc.cu (tcgen05)
+bool k_srp_tensor_supported(int M);
+size_t k_srp_tensor_workspace_bytes(long long BT, int M, int N, int D);
+int k_srp_tensor_ws(const float2 *spec, int B, int T, int M, int N, const uint64_t *mic_fx, int D, float *srp, void *workspace, size_t ws_bytes,
+                    cudaStream_t st);
+int k_srp_tensor(const float2 *spec, int B, int T, int M, int N, const uint64_t *mic_fx, int D, float *srp, cudaStream_t st);
+
 // mask.cu
 int k_mask_stats(const float2 *spec, long long BT, int N, const float *H2, int nb, float *stats, cudaStream_t st);
 int k_mask_scan(const float *stats, int B, int T, int N, int nb, int method, int alg, const float *thresholds, float *Q, float *noise,

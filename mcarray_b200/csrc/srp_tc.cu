@@ -28,6 +28,12 @@
 
 #include <cuda.h>
 
+#define OK_RC(call)        \
+  do {                     \
+    int rc__ = (call);     \
+    if (rc__) return rc__; \
+  } while (0)
+
 namespace mcag {
 
 constexpr int TC_BM = 128;        // frames per tile (UMMA M)
@@ -354,56 +360,97 @@ template <int NKC> static void launch_tc(int grid, cudaStream_t st, const CUtens
   kern<<<grid, TC_THREADS, TC_SMEM, st>>>(hi, lo, p);
 }
 
-// Supported shapes: M in {16, 32, 48, 64}; anything else runs the CUDA-core tile kernel (still on the GPU).
-int k_srp_tensor(const float2 *spec, int B, int T, int M, int N, const uint64_t *mic_fx, int D, float *srp, cudaStream_t st) {
-  if (B <= 0 || T <= 0) return 0;
-  if (M % 16 != 0 || M < 16 || M > 64) return k_srp_channel(spec, B, T, M, N, mic_fx, D, srp, st);
-  const long long BT = (long long)B * T, BTpad = (BT + TC_BM - 1) / TC_BM * TC_BM;
+// Work decomposition shared by the workspace query and the launcher.
+static void tc_plan(long long BT, int M, int N, int D, TcParams &p, long long &BTpad) {
+  BTpad = (BT + TC_BM - 1) / TC_BM * TC_BM;
   const int K = N / 2 + 1;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  TcParams p;
-  p.BT = BT; p.D = D; p.M = M; p.K = K; p.mic_fx = mic_fx;
+  p.BT = BT; p.D = D; p.M = M; p.K = K;
   p.n_tt = (int)(BTpad / TC_BM); p.n_dt = (D + TC_BD - 1) / TC_BD;
   // bin ranges: enough work items for ~4 waves of persistent CTAs, at least 16 bins each
-  long long tiles = (long long)p.n_tt * p.n_dt;
+  const long long tiles = (long long)p.n_tt * p.n_dt;
   int n_ks = (int)((4LL * sms + tiles - 1) / tiles);
   if (n_ks > K / 16) n_ks = K / 16;
   if (n_ks < 1) n_ks = 1;
   p.bins_per_range = (K + n_ks - 1) / n_ks;
   p.n_ks = (K + p.bins_per_range - 1) / p.bins_per_range;
-  const size_t u_bytes = (size_t)K * BTpad * 2 * M * sizeof(float), part_bytes = (size_t)p.n_ks * BT * D * sizeof(float);
-  float *Uhi = nullptr, *Ulo = nullptr, *partial = nullptr, *nzsum = nullptr;
-  if (cudaMallocAsync(&Uhi, u_bytes, st) != cudaSuccess || cudaMallocAsync(&Ulo, u_bytes, st) != cudaSuccess ||
-      cudaMallocAsync(&partial, part_bytes, st) != cudaSuccess || cudaMallocAsync(&nzsum, (size_t)BT * sizeof(float), st) != cudaSuccess)
-    return mcag_set_cuda_error(cudaGetLastError());
+}
+bool k_srp_tensor_supported(int M) { return M % 16 == 0 && M >= 16 && M <= 64; }
+// bytes of scratch k_srp_tensor_ws needs for up to BT frames: [U_hi | U_lo | partial | nzsum], each 1 KB aligned
+size_t k_srp_tensor_workspace_bytes(long long BT, int M, int N, int D) {
+  if (!k_srp_tensor_supported(M) || BT <= 0) return 0;
+  TcParams p; long long BTpad;
+  tc_plan(BT, M, N, D, p, BTpad);
+  auto al = [](size_t n) { return (n + 1023) & ~(size_t)1023; };
+  const int K = N / 2 + 1;
+  // n_ks shrinks as BT grows, so the partial maps of any smaller call fit when sized with the largest bin-range count
+  return 2 * al((size_t)K * BTpad * 2 * M * 4) + al((size_t)(K / 16 > 0 ? K / 16 : 1) * BT * D * 4) + al((size_t)BT * 4);
+}
+
+// Supported shapes: M in {16, 32, 48, 64}; anything else runs the CUDA-core tile kernel (still on the GPU).
+int k_srp_tensor_ws(const float2 *spec, int B, int T, int M, int N, const uint64_t *mic_fx, int D, float *srp, void *workspace, size_t ws_bytes,
+                    cudaStream_t st) {
+  if (B <= 0 || T <= 0) return 0;
+  if (!k_srp_tensor_supported(M)) return k_srp_channel(spec, B, T, M, N, mic_fx, D, srp, st);
+  const long long BT = (long long)B * T;
+  TcParams p; long long BTpad;
+  tc_plan(BT, M, N, D, p, BTpad);
+  p.mic_fx = mic_fx;
+  const int K = p.K;
+  auto al = [](size_t n) { return (n + 1023) & ~(size_t)1023; };
+  const size_t u_bytes = al((size_t)K * BTpad * 2 * M * sizeof(float)), part_bytes = al((size_t)p.n_ks * BT * D * sizeof(float));
+  if (2 * u_bytes + part_bytes + al((size_t)BT * 4) > ws_bytes) return mcag_set_error(4, "srp_tensor: workspace too small");
+  unsigned char *w = static_cast<unsigned char *>(workspace);
+  float *Uhi = reinterpret_cast<float *>(w), *Ulo = reinterpret_cast<float *>(w + u_bytes), *partial = reinterpret_cast<float *>(w + 2 * u_bytes),
+        *nzsum = reinterpret_cast<float *>(w + 2 * u_bytes + part_bytes);
   p.partial = partial;
-  if (BTpad != BT) { cudaMemsetAsync(Uhi, 0, u_bytes, st); cudaMemsetAsync(Ulo, 0, u_bytes, st); }
+  if (BTpad != BT) {   // rows of the last frame tile beyond BT must read as zeros
+    for (int k = 0; k < K; ++k) {
+      cudaMemsetAsync(Uhi + ((size_t)k * BTpad + BT) * 2 * M, 0, (size_t)(BTpad - BT) * 2 * M * 4, st);
+      cudaMemsetAsync(Ulo + ((size_t)k * BTpad + BT) * 2 * M, 0, (size_t)(BTpad - BT) * 2 * M * 4, st);
+    }
+  }
   srp_prepare_kernel<<<(unsigned)BT, 256, 0, st>>>(spec, BT, BTpad, M, N, Uhi, Ulo, nzsum);
   MCAG_CHECK_LAUNCH();
   CUtensorMap map_hi, map_lo;
-  int rc = encode_map(&map_hi, Uhi, BTpad, M, K);
-  if (!rc) rc = encode_map(&map_lo, Ulo, BTpad, M, K);
-  if (!rc) {
-    const long long items = (long long)p.n_tt * p.n_dt * p.n_ks;
-    const int grid = (int)(items < sms ? items : sms);
-    switch (M / 16) {
-      case 1: launch_tc<1>(grid, st, map_hi, map_lo, p); break;
-      case 2: launch_tc<2>(grid, st, map_hi, map_lo, p); break;
-      case 3: launch_tc<3>(grid, st, map_hi, map_lo, p); break;
-      default: launch_tc<4>(grid, st, map_hi, map_lo, p); break;
-    }
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) rc = mcag_set_cuda_error(e);
+  OK_RC(encode_map(&map_hi, Uhi, BTpad, M, K));
+  OK_RC(encode_map(&map_lo, Ulo, BTpad, M, K));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long items = (long long)p.n_tt * p.n_dt * p.n_ks;
+  const int grid = (int)(items < sms ? items : sms);
+  switch (M / 16) {
+    case 1: launch_tc<1>(grid, st, map_hi, map_lo, p); break;
+    case 2: launch_tc<2>(grid, st, map_hi, map_lo, p); break;
+    case 3: launch_tc<3>(grid, st, map_hi, map_lo, p); break;
+    default: launch_tc<4>(grid, st, map_hi, map_lo, p); break;
   }
-  if (!rc) {
-    const long long n = BT * D;
-    srp_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, p.n_ks, BT, D, nzsum, srp);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) rc = mcag_set_cuda_error(e);
+  MCAG_CHECK_LAUNCH();
+  const long long n = BT * D;
+  srp_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, p.n_ks, BT, D, nzsum, srp);
+  MCAG_CHECK_LAUNCH();
+  return 0;
+}
+
+// kernel-level entry without a caller-owned workspace: stream-ordered scratch from the device's memory pool
+int k_srp_tensor(const float2 *spec, int B, int T, int M, int N, const uint64_t *mic_fx, int D, float *srp, cudaStream_t st) {
+  if (B <= 0 || T <= 0) return 0;
+  if (!k_srp_tensor_supported(M)) return k_srp_channel(spec, B, T, M, N, mic_fx, D, srp, st);
+  static bool pool_kept = false;
+  if (!pool_kept) {   // keep freed scratch in the pool across synchronisations instead of returning it to the driver
+    int dev = 0; cudaGetDevice(&dev);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) { unsigned long long keep = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); }
+    pool_kept = true;
   }
-  cudaFreeAsync(Uhi, st); cudaFreeAsync(Ulo, st); cudaFreeAsync(partial, st); cudaFreeAsync(nzsum, st);
+  const size_t bytes = k_srp_tensor_workspace_bytes((long long)B * T, M, N, D);
+  void *ws = nullptr;
+  if (cudaMallocAsync(&ws, bytes, st) != cudaSuccess) return mcag_set_cuda_error(cudaGetLastError());
+  const int rc = k_srp_tensor_ws(spec, B, T, M, N, mic_fx, D, srp, ws, bytes, st);
+  cudaFreeAsync(ws, st);
   return rc;
 }
 
