@@ -200,17 +200,34 @@ class Cfg4(Workload):
         return out
 
 
-WORKLOADS = {"cfg2": Cfg2, "cfg4": Cfg4, "cfg5": Cfg5}
+class Cfg4Sharded(Cfg4):
+    """cfg4 with the direction grid split over the GPUs: same input on every rank, D/G directions each, one NCCL MAX all-reduce of the
+    packed per-frame (peak, cell) keys.  Strong scaling: the total work is fixed as N grows."""
+    name = Cfg4.name + "; direction grid sharded over the GPUs, one NCCL max-allreduce per step"
+    sharded_grid = True
+
+    def make(self, mb, B, T):
+        return mb.sharding.ShardedSrpPhat(self.fs, self.xyz(), self.N, self.dirs(), n_streams=B, max_frames_per_call=T)
+
+    def host_input(self, rank, B, n, unique=8):
+        return super().host_input(0, B, n, unique)                  # every rank sees the same array signals
+
+    def fetch_result(self, p):
+        return None
+
+
+WORKLOADS = {"cfg2": Cfg2, "cfg4": Cfg4, "cfg4s": Cfg4Sharded, "cfg5": Cfg5}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock and throttle reasons DURING the timed region: NVML polled every ~2 ms from a thread (the same counters
+    """SM clock and throttle reasons DURING the timed region: NVML polled every ~25 ms from a thread (the same counters
     the nvidia-smi recipe in B200_PROFILING.md prints; nvidia-smi's 100 ms loop is too coarse for a tens-of-ms region)."""
     BITS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "hw_power_brake": 0x80}
 
-    def __init__(self, gpu_index):
-        self.gpu, self.rows, self._stop, self.thread, self.err = gpu_index, [], threading.Event(), None, None
+    def __init__(self, gpu_index, period=0.025):
+        # NVML queries take driver locks that kernel / NCCL launches also need: poll gently (25 ms), not in a tight loop
+        self.gpu, self.rows, self._stop, self.thread, self.err, self.period = gpu_index, [], threading.Event(), None, None, period
 
     def _run(self):
         try:
@@ -222,8 +239,8 @@ class ClockSampler:
             mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
             while not self._stop.is_set():
                 self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), mx, nv.nvmlDeviceGetPowerUsage(h) / 1e3,
-                                  nv.nvmlDeviceGetCurrentClocksEventReasons(h), nv.nvmlDeviceGetUtilizationRates(h).gpu))
-                time.sleep(0.002)
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(h)))
+                time.sleep(self.period)
             nv.nvmlShutdown()
         except Exception as e:  # noqa: BLE001
             self.err = repr(e)
@@ -241,7 +258,7 @@ class ClockSampler:
         sm = [r[0] for r in self.rows]
         reasons = sorted({name for r in self.rows for name, bit in self.BITS.items() if r[3] & bit})
         return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(sm), "power_w_max": float(max(r[2] for r in self.rows)), "how": "NVML polled every ~2 ms during the timed region"}
+                "samples": len(sm), "power_w_max": float(max(r[2] for r in self.rows)), "how": "NVML polled every ~25 ms during the timed region"}
 
 
 def profile_read(p, reset=True):
@@ -338,7 +355,9 @@ def main():
     input_bytes = rows * n * 4
 
     mb.set_default_device(local)
-    p = wl.make(mb, B, T)
+    sharded = getattr(wl, "sharded_grid", False)
+    sp = wl.make(mb, B, T) if sharded else None                   # grid-sharded processor: wraps a local handle + the all-reduce
+    p = sp.local if sharded else wl.make(mb, B, T)
     stream = torch.cuda.ExternalStream(capi.lib().mcag_stream(p.handle), device=torch.device("cuda", local))
     d_out = None
     if p.info.n_out_channels:
@@ -351,7 +370,10 @@ def main():
 
     def step_device():
         p.flush_input()
-        p.process_device(d_in, n, n, d_out, T * wl.hop if d_out is not None else 0)
+        if sharded:
+            sp.process_device(d_in, n, n)                           # local slice + packed arg-max + NCCL MAX all-reduce
+        else:
+            p.process_device(d_in, n, n, d_out, T * wl.hop if d_out is not None else 0)
 
     def max_over_ranks(ms):
         if world == 1:
@@ -384,7 +406,8 @@ def main():
     prof = profile_read(p)
     capi.check(capi.lib().mcag_profile_enable(p.handle, 0))
     ms_step = ms_total / args.steps
-    value = units_rank * world / (ms_step * 1e-3)
+    units_job = units_rank if sharded else units_rank * world      # sharded grid: every rank works on the same samples
+    value = units_job / (ms_step * 1e-3)
 
     # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ------------------------------------------
     e2e = None
@@ -397,6 +420,10 @@ def main():
 
         def step_e2e():
             p.flush_input()
+            if sharded:
+                p.flush_input()
+                capi.check(capi.lib().mcag_process_packed_f32(p.handle, C.c_void_p(pin.data_ptr()), C.c_longlong(n), C.c_int(n), None, C.c_longlong(0), C.byref(nout)))
+                return [t.cpu() for t in sp._reduce()]
             capi.check(capi.lib().mcag_process_packed_f32(p.handle, C.c_void_p(pin.data_ptr()), C.c_longlong(n), C.c_int(n),
                                                           C.c_void_p(out_host.data_ptr()) if out_host is not None else None,
                                                           C.c_longlong(T * wl.hop if out_host is not None else 0), C.byref(nout)))
@@ -414,7 +441,7 @@ def main():
         wall_ms = (time.perf_counter() - t0) * 1e3
         barrier()
         ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), wall_ms)) / args.steps
-        e2e = {"value": units_rank * world / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": input_bytes, "d2h_bytes_per_step": int(res_bytes),
+        e2e = {"value": units_job / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": input_bytes, "d2h_bytes_per_step": int(res_bytes),
                "ms_per_step": ms_e2e}
 
     if rank != 0:
@@ -433,6 +460,8 @@ def main():
     bytes_per_launch = kb.get(dom, wl.pipeline_bytes_per_frame()) * B * T
     achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
     flops = getattr(wl, "kernel_flops_per_frame", lambda: {})().get(dom)
+    if sharded and flops:
+        flops = flops * (sp.d1 - sp.d0) / wl.D                     # this rank contracts only its slice of the direction grid
     if getattr(wl, "bound", "hbm") == "tensor" and flops:
         # 3xTF32: every algorithmic flop is issued three times on the TF32 pipe; TF32 dense peak = half the measured bf16 GEMM rate
         issued = 3.0 * flops * B * T / (per_launch_ms * 1e-3) / 1e12
@@ -458,11 +487,12 @@ def main():
             roofline["traffic"] = json.load(f).get(args.workload, {}).get(dom)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl.name, "streams_per_gpu": B, "frames_per_stream_per_step": T, "samples_per_channel_per_step": n,
                        "input_bytes_per_gpu": input_bytes, "l2_policy": "inputs larger than L2 (input + intermediates per step >> 126 MB)",
-                       "parallelism": f"independent array streams sharded over {world} GPU(s), no collective"},
-            "xrt_aggregate": (B * world * T * wl.hop / wl.fs) / (ms_step * 1e-3), "xrt_per_stream": (T * wl.hop / wl.fs) / (ms_step * 1e-3),
+                       "parallelism": (f"direction grid sharded over {world} GPU(s), one NCCL max-allreduce per step" if sharded else
+                                       f"independent array streams sharded over {world} GPU(s), no collective")},
+            "xrt_aggregate": (B * (1 if sharded else world) * T * wl.hop / wl.fs) / (ms_step * 1e-3), "xrt_per_stream": (T * wl.hop / wl.fs) / (ms_step * 1e-3),
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
     if e2e:
         line["e2e"] = e2e

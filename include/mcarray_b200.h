@@ -185,6 +185,9 @@ int mcag_k_gcc_tau(const void *d_spec, int B, int T, int M, int N, const uint64_
 int mcag_k_pair_sum(const float *d_corr, long long BT, int P, int D, float scale, float *d_esum, void *stream);
 int mcag_k_energy_scan(const float *d_esum, int B, int T, int D, float a, const unsigned char *d_active, float *d_state, float *d_energy, void *stream);
 int mcag_k_select_doa(const float *d_energy, long long BT, int D, int n_pairs, int S, int32_t *d_idx, float *d_prob, void *stream);
+/* per-frame (max, first argmax) of an energy-map slice [rows][D] whose first column is global direction d_offset, packed as
+ * ordered(E) << 31 | (0x7FFFFFFF - d): an int64 MAX all-reduce over the slices of a sharded grid gives the global arg-max cell */
+int mcag_k_argmax_pack(const float *d_map, long long rows, int D, int d_offset, long long *d_packed, void *stream);
 int mcag_k_ds_fan(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_steer_fx, int D, void *d_out, void *stream);
 int mcag_k_srp_channel(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_mic_fx, int D, float *d_srp, void *stream);
 int mcag_k_srp_tensor(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_mic_fx, int D, float *d_srp, void *stream);

@@ -5,3 +5,4 @@ This Python package is the thin ctypes mirror used by the tests and bench.py."""
 from . import _capi as capi  # noqa: F401
 from .processors import (DelayAndSumFan, FastBinauralMasking, FreqGCCBinauralLocalisation, Processor,  # noqa: F401
                          SourceLocalisation, SourceSeparationAndLocalisation, SrpPhat, TdoaEstimator, set_default_device)
+from . import sharding  # noqa: F401,E402

@@ -924,6 +924,9 @@ int mcag_k_energy_scan(const float *d_esum, int B, int T, int D, float a, const 
 int mcag_k_select_doa(const float *d_energy, long long BT, int D, int n_pairs, int S, int32_t *d_idx, float *d_prob, void *stream) {
   return k_select_doa(d_energy, BT, D, n_pairs, S, d_idx, d_prob, (cudaStream_t)stream);
 }
+int mcag_k_argmax_pack(const float *d_map, long long rows, int D, int d_offset, long long *d_packed, void *stream) {
+  return k_argmax_pack(d_map, rows, D, d_offset, d_packed, (cudaStream_t)stream);
+}
 int mcag_k_ds_fan(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_steer_fx, int D, void *d_out, void *stream) {
   return k_ds_fan((const float2 *)d_spec, B, T, M, N, d_steer_fx, D, (float2 *)d_out, (cudaStream_t)stream);
 }

@@ -95,6 +95,29 @@ __global__ void row_argmax_kernel(const float *__restrict__ x, long long rows, i
   if (lane == 0) idx[row] = bi;
 }
 
+// Per-frame first-maximum argmax of a (slice of a) direction map, packed so that an integer MAX reduction over slices (one
+// NCCL all-reduce when the grid is sharded over GPUs) yields the global maximum with ties going to the lowest direction index:
+//   packed = ordered(E) << 31 | (0x7FFFFFFF - d_global),   ordered() = the monotone float -> uint32 map; always >= 0 as int64.
+__global__ void argmax_pack_kernel(const float *__restrict__ x, long long rows, int D, int d_offset, long long *__restrict__ packed) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float bv = -3.0e38f; int bi = 0x7fffffff;
+  for (int i = lane; i < D; i += 32) { float v = x[row * D + i]; if (v > bv) { bv = v; bi = i; } }
+  warp_argmax(bv, bi);
+  if (lane == 0) {
+    uint32_t u = __float_as_uint(bv);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    packed[row] = (long long)(((unsigned long long)u << 31) | (unsigned long long)(0x7FFFFFFF - (d_offset + bi)));
+  }
+}
+int k_argmax_pack(const float *x, long long rows, int D, int d_offset, long long *packed, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  argmax_pack_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, rows, D, d_offset, packed);
+  MCAG_CHECK_LAUNCH();
+  return 0;
+}
+
 int k_pair_sum(const float *corr, long long BT, int P, int D, float scale, float *esum, cudaStream_t st) {
   const long long n = BT * D;
   if (n <= 0) return 0;

@@ -22,6 +22,7 @@ int k_gcc_tau(const float2 *spec, int B, int T, int M, int N, const uint64_t *pa
 // doa.cu
 int k_pair_sum(const float *corr, long long BT, int P, int D, float scale, float *esum, cudaStream_t st);
 int k_energy_scan(const float *esum, int B, int T, int D, float a, const unsigned char *active, float *state, float *energy, cudaStream_t st);
+int k_argmax_pack(const float *x, long long rows, int D, int d_offset, long long *packed, cudaStream_t st);
 int k_select_doa(const float *energy, long long BT, int D, int n_pairs, int S, int32_t *idx, float *prob, cudaStream_t st);
 int k_curve_scan_argmax(const float *corr, int B, int T, int D, float keep_first, float mem, const unsigned char *active, float *state,
                         unsigned char *started, float *curves, int32_t *idx, cudaStream_t st);

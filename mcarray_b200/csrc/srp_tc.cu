@@ -344,7 +344,24 @@ __global__ void srp_reduce_kernel(const float *__restrict__ partial, int n_part,
   srp[i] = 0.5f * (acc - nzsum[i / D]);
 }
 
+// cuTensorMapEncodeTiled is a driver entry point: fetched through the runtime so the library does not link libcuda.so
+// (it must still load, and fail loudly at mcag_create, on a box without a GPU driver).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
 static int encode_map(CUtensorMap *map, const float *base, long long BTpad, int M, int K) {
+  EncodeTiledFn cuTensorMapEncodeTiled = encode_tiled_fn();
+  if (!cuTensorMapEncodeTiled) return mcag_set_error(2, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[3] = {(cuuint64_t)(2 * M), (cuuint64_t)BTpad, (cuuint64_t)K};
   cuuint64_t strides[2] = {(cuuint64_t)(2 * M) * 4, (cuuint64_t)BTpad * (2 * M) * 4};
   cuuint32_t box[3] = {TC_KC, TC_BM, 1}, estr[3] = {1, 1, 1};
