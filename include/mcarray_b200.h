@@ -108,11 +108,20 @@ typedef struct {
   int n_bands;            /* 45 (FastBinauralMasking.h:111) */
   const double *band_coefs;      /* [n_bands][N/2+1] real filter-bank magnitudes */
   const double *band_thresholds; /* [n_bands] cos(w_b d sin(phi)/c) (FastBinauralMasking.cpp:342-366) */
+
+  /* SSL / SL: how the pair sum of SteeringBeamforming::computeCorrelations (SteeringBeamforming.cpp:104-144) is evaluated.
+   * 0 auto: the channel form on the tensor cores (sum_{i<j} Re G_ij e^{jw tau_ij} = (|sum_m U_m e^{-jw tau_m}|^2 - nz)/2)
+   *         when the pair delays are consistent with per-microphone delays (tau_ij = tau_j - tau_i within 2e-5 samples, true for
+   *         the reference's ascending linear arrays), M is 16/32/48/64 and MCAG_EMIT_CORR is not set; the pair form otherwise.
+   * 1 pair form always (pair by pair in the reference's order; MCAG_OUT_CORR is only produced by this form).
+   * 2 channel form required: mcag_create fails if the geometry / channel count does not allow it. */
+  int srp_form;
 } mcag_config;
 
 typedef struct {
   int frame_size, window_size, hop, analysis_length, one_sided_length, n_channels, n_streams, max_latency;
   int n_dirs, n_pairs, n_sources, n_out_channels, spectrum_pitch, max_frames_per_call;
+  int srp_form;           /* SSL / SL: 1 = pair form, 2 = channel form (what mcag_create chose); 0 for other kinds */
 } mcag_info;
 
 const char *mcag_last_error(void);

@@ -24,13 +24,14 @@ class Config(C.Structure):
         ("energy_memory", C.c_float), ("corr_memory", C.c_float), ("use_power_floor", C.c_int), ("noise_margin_db", C.c_float),
         ("floor_seconds", C.c_float), ("floor_ccs_power", C.c_int), ("noise_preestimated", C.c_int), ("max_lag", C.c_int),
         ("mask_method", C.c_int), ("mask_alg", C.c_int), ("n_bands", C.c_int), ("band_coefs", c_dp), ("band_thresholds", c_dp),
+        ("srp_form", C.c_int),
     ]
 
 
 class Info(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "frame_size", "window_size", "hop", "analysis_length", "one_sided_length", "n_channels", "n_streams", "max_latency",
-        "n_dirs", "n_pairs", "n_sources", "n_out_channels", "spectrum_pitch", "max_frames_per_call")]
+        "n_dirs", "n_pairs", "n_sources", "n_out_channels", "spectrum_pitch", "max_frames_per_call", "srp_form")]
 
 
 _lib = None

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -169,6 +170,7 @@ struct mcag_proc_s {
   mcag_config cfg;
   int B, M, N, hop, K, KP, P, D, S, Cs /* synthesised channels */, Cout /* channels the caller sees */, Tmax, L;
   int rows;
+  int srp_form = 0;   // SSL / SL: 1 pair form, 2 channel form on the tensor cores (mcag_config::srp_form resolved at create)
   cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
   cudaEvent_t ev_in[8] = {nullptr}, ev_done[8] = {nullptr};
   long long launches = 0, frames_total = 0;
@@ -324,7 +326,31 @@ int mcag_create(const mcag_config *cfg, mcag_proc *out) {
     std::vector<double> turns(P * D);
     for (size_t i = 0; i < P * D; ++i) turns[i] = cfg->pair_tau[i] / (double)N;   // exp(+j 2 pi k tau / N)
     if ((rc = upload_fx(p->pair_fx, turns.data(), turns.size(), st))) return fail(rc);
-    if ((rc = p->corr.alloc(sizeof(float) * B * T * P * D))) return fail(rc);
+    if (loc) {
+      // Channel form: valid when tau_ij(d) = tau_j(d) - tau_i(d) for per-microphone delays tau_m (tau_0 = 0,
+      // tau_j = tau_0j).  The reference's scalar pair distances (SteeringBeamforming.cpp:67-73) satisfy this for linear arrays with
+      // ascending coordinates, up to the float rounding of doaToDelayFarFieldSamples (~2e-6 samples).
+      std::vector<double> mt(M * D, 0.0);
+      for (size_t j = 1; j < M; ++j) for (size_t d = 0; d < D; ++d) mt[j * D + d] = cfg->pair_tau[(j - 1) * D + d];
+      double worst = 0.0;
+      size_t pi = 0;
+      for (size_t i = 0; i < M; ++i) for (size_t j = i + 1; j < M; ++j, ++pi) for (size_t d = 0; d < D; ++d)
+        worst = std::fmax(worst, std::fabs(cfg->pair_tau[pi * D + d] - (mt[j * D + d] - mt[i * D + d])));
+      const bool can = worst <= 2e-5 && k_srp_tensor_supported(p->M);
+      if (cfg->srp_form == 2 && !can)
+        return fail(mcag_set_error(MCAG_ERR_INVALID, "srp_form = channel: needs 16/32/48/64 channels and pair delays consistent with per-microphone delays"));
+      if (cfg->srp_form == 2 && (cfg->emit & MCAG_EMIT_CORR))
+        return fail(mcag_set_error(MCAG_ERR_INVALID, "srp_form = channel does not produce per-pair correlations (MCAG_EMIT_CORR)"));
+      p->srp_form = (cfg->srp_form == 2 || (cfg->srp_form == 0 && can && !(cfg->emit & MCAG_EMIT_CORR))) ? 2 : 1;
+      if (p->srp_form == 2) {
+        std::vector<double> mturns(D * M);   // device layout [D][M], exp(-j 2 pi k tau_m / N)
+        for (size_t m = 0; m < M; ++m) for (size_t d = 0; d < D; ++d) mturns[d * M + m] = -mt[m * D + d] / (double)N;
+        if ((rc = upload_fx(p->mic_fx, mturns.data(), mturns.size(), st))) return fail(rc);
+        if ((rc = p->srp_ws.alloc(k_srp_tensor_workspace_bytes((long long)B * T, p->M, N, p->D)))) return fail(rc);
+      }
+    }
+    if (p->srp_form != 2)
+      if ((rc = p->corr.alloc(sizeof(float) * B * T * P * D))) return fail(rc);
   }
   if (loc || kind == MCAG_KIND_SRP) {
     if ((rc = p->esum.alloc(sizeof(float) * B * T * D))) return fail(rc);
@@ -427,7 +453,7 @@ int mcag_get_info(mcag_proc p, mcag_info *i) {
   if (!p || !i) return mcag_set_error(MCAG_ERR_INVALID, "null argument");
   i->frame_size = p->hop; i->window_size = p->N; i->hop = p->hop; i->analysis_length = p->N + 2; i->one_sided_length = p->K;
   i->n_channels = p->M; i->n_streams = p->B; i->max_latency = p->N; i->n_dirs = p->D; i->n_pairs = p->P; i->n_sources = p->S;
-  i->n_out_channels = p->Cout; i->spectrum_pitch = p->KP; i->max_frames_per_call = p->Tmax;
+  i->n_out_channels = p->Cout; i->spectrum_pitch = p->KP; i->max_frames_per_call = p->Tmax; i->srp_form = p->srp_form;
   return MCAG_OK;
 }
 
@@ -500,7 +526,10 @@ int mcag_dev_download(void *h_dst, const void *d_src, long long bytes) {
 // ----------------------------------------------------------------------------------------------------------------------
 // Streams [b0, b0 + nb) of the handle; every result / state array is stream-major, so a sub-batch is a pointer offset.
 // process_host uses this to overlap the host->device copy of one group of streams with the kernels of the previous one.
-static int run_frames(mcag_proc p, const float *x_all, long long pitch, int T, int b0, int nb) {
+// ext_out (optional): the caller's device buffer [B*ext_rows][ext_pitch]; the synthesis kernel writes its Cs channels of every stream
+// straight into it instead of out_dev.
+static int run_frames(mcag_proc p, const float *x_all, long long pitch, int T, int b0, int nb, float *ext_out = nullptr, long long ext_pitch = 0,
+                      int ext_rows = 0) {
   cudaStream_t st = p->stream;
   const int B = nb, M = p->M, N = p->N, hop = p->hop, D = p->D, P = p->P, S = p->S, kind = p->cfg.kind, KP = p->KP, Cs = p->Cs;
   const long long BT = (long long)B * T, o = b0;   // o: stream offset
@@ -549,22 +578,37 @@ static int run_frames(mcag_proc p, const float *x_all, long long pitch, int T, i
   auto synth = [&](const float2 *src, int C) -> int {
     PROF(MCAG_PROF_ISTFT);
     const long long ov = N - hop;
-    OK(k_istft(src, B, T, C, C, N, hop, win, tw, p->tail[p->tail_cur].as<float>() + o * C * ov, p->tail[p->tail_cur ^ 1].as<float>() + o * C * ov,
-               p->out_dev.as<float>() + o * C * T * hop, (long long)T * hop, st));
+    if (ext_out)
+      OK(k_istft(src, B, T, C, C, N, hop, win, tw, p->tail[p->tail_cur].as<float>() + o * C * ov, p->tail[p->tail_cur ^ 1].as<float>() + o * C * ov,
+                 ext_out + o * ext_rows * ext_pitch, ext_pitch, ext_rows, st));
+    else
+      OK(k_istft(src, B, T, C, C, N, hop, win, tw, p->tail[p->tail_cur].as<float>() + o * C * ov, p->tail[p->tail_cur ^ 1].as<float>() + o * C * ov,
+                 p->out_dev.as<float>() + o * C * T * hop, (long long)T * hop, C, st));
     p->launches++;
     return MCAG_OK;
   };
 
   if (kind == MCAG_KIND_SSL || kind == MCAG_KIND_SL) {
-    float *corr = p->corr.as<float>() + o * T * P * D;
-    {
-      PROF(MCAG_PROF_GCC_TAU);
-      OK(k_gcc_tau(spec, B, T, M, N, p->pair_fx.as<uint64_t>(), D, corr, st));
-      p->launches += (D <= 40) ? 1 : (D + 63) / 64;
-    }
-    {
+    const float a = p->cfg.energy_memory, b = 1.0f - p->cfg.energy_memory;   // float arithmetic as SteeringBeamforming.cpp:134,139
+    if (p->srp_form == 2) {
+      // channel form: the whole pair sum of computeCorrelations is one tcgen05 contraction per bin (srp_tc.cu)
+      {
+        PROF(MCAG_PROF_SRP);
+        OK(k_srp_tensor_ws(spec, B, T, M, N, p->mic_fx.as<uint64_t>(), D, esum, p->srp_ws.p, p->srp_ws.bytes, st));
+        p->launches += 3;
+      }
       PROF(MCAG_PROF_ENERGY);
-      const float a = p->cfg.energy_memory, b = 1.0f - p->cfg.energy_memory;   // float arithmetic as SteeringBeamforming.cpp:134,139
+      OK(k_pair_sum(esum, BT, 1, D, b, energy, st));
+      OK(k_energy_scan(energy, B, T, D, a, active, energy_state, energy, st));
+      p->launches += 2;
+    } else {
+      float *corr = p->corr.as<float>() + o * T * P * D;
+      {
+        PROF(MCAG_PROF_GCC_TAU);
+        OK(k_gcc_tau(spec, B, T, M, N, p->pair_fx.as<uint64_t>(), D, corr, st));
+        p->launches += (D <= 40) ? 1 : (D + 63) / 64;
+      }
+      PROF(MCAG_PROF_ENERGY);
       OK(k_pair_sum(corr, BT, P, D, b, esum, st));
       OK(k_energy_scan(esum, B, T, D, a, active, energy_state, energy, st));
       p->launches += 2;
@@ -644,7 +688,8 @@ static int frames_for(const mcag_proc p, int nsamples) {
 }
 
 // core: new samples are on the device at d_new (rows x pitch).  Handles the FIFO, runs the frames, leaves audio in out_dev.
-static int process_device_core(mcag_proc p, const float *d_new, long long pitch, int nsamples, int *T_out) {
+static int process_device_core(mcag_proc p, const float *d_new, long long pitch, int nsamples, int *T_out, float *d_out = nullptr,
+                               long long out_pitch = 0) {
   cudaStream_t st = p->stream;
   const int T = frames_for(p, nsamples);
   if (T > p->Tmax) return mcag_set_error(MCAG_ERR_CAPACITY, "process: more frames than max_frames_per_call");
@@ -657,7 +702,17 @@ static int process_device_core(mcag_proc p, const float *d_new, long long pitch,
     CU(cudaMemcpy2DAsync(cur + p->fill, p->fifo_cap * 4, d_new, pitch * 4, (size_t)nsamples * 4, p->rows, cudaMemcpyDeviceToDevice, st));
     x = cur; xp = p->fifo_cap;
   }
-  if (T > 0) { OK(run_frames(p, x, xp, T, 0, p->B)); if (p->Cs > 0) p->tail_cur ^= 1; }
+  if (T > 0) {
+    float *ext = nullptr;
+    if (p->Cs > 0 && d_out) {
+      if ((long long)T * p->hop > out_pitch) return mcag_set_error(MCAG_ERR_CAPACITY, "process: output pitch too small");
+      // channels >= Cs are zeros (BeamformingSeparationAndLocalisation.cpp:117-118); the synthesis kernel then writes the first Cs
+      if (p->Cs != p->Cout) CU(cudaMemset2DAsync(d_out, out_pitch * 4, 0, (size_t)T * p->hop * 4, (size_t)p->B * p->Cout, st));
+      ext = d_out;
+    }
+    OK(run_frames(p, x, xp, T, 0, p->B, ext, out_pitch, p->Cout));
+    if (p->Cs > 0) p->tail_cur ^= 1;
+  }
   // carry the unconsumed samples
   const long long have = (long long)p->fill + nsamples, consumed = (long long)T * p->hop, left = have - consumed;
   if (left > 0) {
@@ -782,18 +837,35 @@ static int process_host(mcag_proc p, const Tio *const *in, const Tio *in_packed,
   p->fill = (int)left;
   p->frames_last = T;
   p->frames_total += T;
+  if (want_audio && nout > 0 && Cout > Cs) {
+    // channels >= Cs are zeros (BeamformingSeparationAndLocalisation.cpp:117-118): filled by the host while the device works
+    std::vector<Tio *> zr;
+    for (int b = 0; b < B; ++b)
+      for (int ch = Cs; ch < Cout; ++ch) {
+        Tio *dst = out_packed ? out_packed + ((long long)b * Cout + ch) * out_pitch : out[(long long)b * Cout + ch];
+        if (dst) zr.push_back(dst);
+      }
+    const size_t row_bytes = (size_t)nout * sizeof(Tio);
+    const int nthr = (zr.size() * row_bytes >= ((size_t)8 << 20)) ? 8 : 1;
+    auto work = [&](int w) { for (size_t i = (size_t)w; i < zr.size(); i += (size_t)nthr) std::memset(zr[i], 0, row_bytes); };
+    if (nthr == 1) work(0);
+    else {
+      std::vector<std::thread> th;
+      for (int w = 1; w < nthr; ++w) th.emplace_back(work, w);
+      work(0);
+      for (auto &t_ : th) t_.join();
+    }
+  }
   CU(cudaStreamSynchronize(st));
   if (want_audio && nout > 0) {
     CU(cudaStreamSynchronize(sout));
-    // channels >= Cs are zeros (BeamformingSeparationAndLocalisation.cpp:117-118); f64 / s16 are converted on the host
+    // f64 / s16 outputs are converted on the host
     const float *src = (const float *)p->pin_out;
     for (int b = 0; b < B; ++b)
-      for (int ch = 0; ch < Cout; ++ch) {
+      for (int ch = 0; ch < Cs && !is_f32; ++ch) {
         Tio *dst = out_packed ? out_packed + ((long long)b * Cout + ch) * out_pitch : out[(long long)b * Cout + ch];
         if (!dst) continue;
-        if (ch >= Cs) {
-          for (int i = 0; i < nout; ++i) dst[i] = (Tio)0;
-        } else if (!is_f32) {
+        {
           const float *s_ = src + ((long long)b * Cs + ch) * nout;
           if (Conv<Tio>::id == 2) for (int i = 0; i < nout; ++i) { float v = nearbyintf(s_[i]); dst[i] = (Tio)(v > 32767.f ? 32767.f : (v < -32768.f ? -32768.f : v)); }
           else for (int i = 0; i < nout; ++i) dst[i] = (Tio)s_[i];
@@ -823,19 +895,8 @@ int mcag_process_device_f32(mcag_proc p, const float *d_in, long long in_pitch, 
   if (!p) return mcag_set_error(MCAG_ERR_INVALID, "null handle");
   CU(cudaSetDevice(p->cfg.device));
   int T = 0;
-  OK(process_device_core(p, d_in, in_pitch, nsamples, &T));
+  OK(process_device_core(p, d_in, in_pitch, nsamples, &T, d_out, out_pitch));
   const int nout = T * p->hop;
-  if (p->Cs > 0 && d_out && nout > 0) {
-    if (nout > out_pitch) return mcag_set_error(MCAG_ERR_CAPACITY, "process: output pitch too small");
-    if (p->Cs == p->Cout) {
-      CU(cudaMemcpy2DAsync(d_out, out_pitch * 4, p->out_dev.p, (size_t)nout * 4, (size_t)nout * 4, (size_t)p->B * p->Cs, cudaMemcpyDeviceToDevice, p->stream));
-    } else {
-      CU(cudaMemset2DAsync(d_out, out_pitch * 4, 0, (size_t)nout * 4, (size_t)p->B * p->Cout, p->stream));
-      for (int b = 0; b < p->B; ++b)
-        CU(cudaMemcpy2DAsync(d_out + (long long)b * p->Cout * out_pitch, out_pitch * 4, p->out_dev.as<float>() + (long long)b * p->Cs * nout, (size_t)nout * 4,
-                             (size_t)nout * 4, p->Cs, cudaMemcpyDeviceToDevice, p->stream));
-    }
-  }
   if (nsamples_out) *nsamples_out = p->Cs > 0 ? nout : 0;
   return MCAG_OK;
 }
@@ -902,7 +963,7 @@ int mcag_k_stft(const float *d_x, long long row_pitch, int rows, int M, int T, i
 }
 int mcag_k_istft(const void *d_spec, int B, int T, int C_in, int C_out, int N, int hop, const float *d_win, const void *d_tw, const float *d_tail_in,
                  float *d_tail_out, float *d_out, long long out_pitch, void *stream) {
-  return k_istft((const float2 *)d_spec, B, T, C_in, C_out, N, hop, d_win, (const float2 *)d_tw, d_tail_in, d_tail_out, d_out, out_pitch, (cudaStream_t)stream);
+  return k_istft((const float2 *)d_spec, B, T, C_in, C_out, N, hop, d_win, (const float2 *)d_tw, d_tail_in, d_tail_out, d_out, out_pitch, C_out, (cudaStream_t)stream);
 }
 int mcag_k_tdoa_lags(const void *d_spec, int B, int T, int M, int N, int max_lag, const void *d_tw, float *d_curves, int32_t *d_lags, float *d_peaks,
                      void *stream) {

@@ -116,6 +116,15 @@ __global__ void __launch_bounds__(256) srp_prepare_kernel(const float2 *__restri
   const int KP = spec_pitch(N), K = N / 2 + 1;
   const long long t = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (t >= BT) {   // rows of the last frame tile beyond BT must read as zeros
+    for (int i = tid; i < K * M; i += 256) {
+      const int k = i / M, m = i - k * M;
+      const long long o = ((long long)k * BTpad + t) * (2 * M) + 2 * m;
+      *reinterpret_cast<float2 *>(Uhi + o) = make_float2(0.f, 0.f);
+      *reinterpret_cast<float2 *>(Ulo + o) = make_float2(0.f, 0.f);
+    }
+    return;
+  }
   float nz = 0.f;
   for (int k0 = 0; k0 < K; k0 += 32) {
     for (int m = warp; m < M; m += 8) {   // coalesced along k
@@ -423,13 +432,7 @@ int k_srp_tensor_ws(const float2 *spec, int B, int T, int M, int N, const uint64
   float *Uhi = reinterpret_cast<float *>(w), *Ulo = reinterpret_cast<float *>(w + u_bytes), *partial = reinterpret_cast<float *>(w + 2 * u_bytes),
         *nzsum = reinterpret_cast<float *>(w + 2 * u_bytes + part_bytes);
   p.partial = partial;
-  if (BTpad != BT) {   // rows of the last frame tile beyond BT must read as zeros
-    for (int k = 0; k < K; ++k) {
-      cudaMemsetAsync(Uhi + ((size_t)k * BTpad + BT) * 2 * M, 0, (size_t)(BTpad - BT) * 2 * M * 4, st);
-      cudaMemsetAsync(Ulo + ((size_t)k * BTpad + BT) * 2 * M, 0, (size_t)(BTpad - BT) * 2 * M * 4, st);
-    }
-  }
-  srp_prepare_kernel<<<(unsigned)BT, 256, 0, st>>>(spec, BT, BTpad, M, N, Uhi, Ulo, nzsum);
+  srp_prepare_kernel<<<(unsigned)BTpad, 256, 0, st>>>(spec, BT, BTpad, M, N, Uhi, Ulo, nzsum);
   MCAG_CHECK_LAUNCH();
   CUtensorMap map_hi, map_lo;
   OK_RC(encode_map(&map_hi, Uhi, BTpad, M, K));

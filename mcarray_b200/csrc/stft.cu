@@ -126,7 +126,7 @@ template <int N, int F, int G>
 __global__ void __launch_bounds__(G *(N / 16)) istft_kernel(const float2 *__restrict__ spec, int C_in, int C_out, int T, int hop,
                                                              const float *__restrict__ win, const float2 *__restrict__ tw_g,
                                                              const float *__restrict__ tail_in, float *__restrict__ tail_out,
-                                                             float *__restrict__ out, long long out_pitch) {
+                                                             float *__restrict__ out, long long out_pitch, int out_rows) {
   constexpr int NC = N / 2, TPF = NC / 8, KP = spec_pitch(N), NT = G * TPF;
   const int R = N / hop;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(G *(N / 16)) istft_kernel(const float2 *__rest
     const long long pos = (long long)seg * hop + n;
     float acc = (tail_in && pos < ov) ? tail_in[(long long)row * ov + pos] : 0.f;
     for (int r = R - 1; r >= 0; --r) acc += s_y[(sl + (R - 1) - r) * N + n + r * hop];
-    if (seg < T) out[(long long)row * out_pitch + pos] = acc;
+    if (seg < T) out[((long long)b * out_rows + c) * out_pitch + pos] = acc;   // out_rows >= C_out rows per stream in the caller's buffer
     else if (tail_out) tail_out[(long long)row * ov + (pos - (long long)T * hop)] = acc;
   }
 }
@@ -213,7 +213,7 @@ template <int N> static int launch_stft(const float *x, long long row_pitch, int
 }
 
 template <int N> static int launch_istft(const float2 *spec, int B, int T, int C_in, int C_out, int hop, const float *win, const float2 *tw,
-                                         const float *tail_in, float *tail_out, float *out, long long out_pitch, cudaStream_t st) {
+                                         const float *tail_in, float *tail_out, float *out, long long out_pitch, int out_rows, cudaStream_t st) {
   constexpr int NC = N / 2, TPF = NC / 8;
   constexpr int F = 8;
   constexpr int G = (TPF >= 128) ? 2 : (256 / TPF);
@@ -223,7 +223,7 @@ template <int N> static int launch_istft(const float2 *spec, int B, int T, int C
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int R = N / hop;
   dim3 grid((T + R - 1 + F - 1) / F, B * C_out);
-  kern<<<grid, G * TPF, smem, st>>>(spec, C_in, C_out, T, hop, win, tw, tail_in, tail_out, out, out_pitch);
+  kern<<<grid, G * TPF, smem, st>>>(spec, C_in, C_out, T, hop, win, tw, tail_in, tail_out, out, out_pitch, out_rows);
   MCAG_CHECK_LAUNCH();
   return 0;
 }
@@ -242,14 +242,15 @@ int k_stft(const float *x, long long row_pitch, int rows, int M, int T, int N, i
 }
 
 int k_istft(const float2 *spec, int B, int T, int C_in, int C_out, int N, int hop, const float *win, const float2 *tw, const float *tail_in,
-            float *tail_out, float *out, long long out_pitch, cudaStream_t st) {
+            float *tail_out, float *out, long long out_pitch, int out_rows, cudaStream_t st) {
   if (T <= 0) return 0;
+  if (out_rows < C_out) out_rows = C_out;
   if (hop <= 0 || hop > N || (N % hop) || N / hop > 4) return mcag_set_error(1, "istft: hop must divide N with N/hop <= 4");
   switch (N) {
-    case 256: return launch_istft<256>(spec, B, T, C_in, C_out, hop, win, tw, tail_in, tail_out, out, out_pitch, st);
-    case 512: return launch_istft<512>(spec, B, T, C_in, C_out, hop, win, tw, tail_in, tail_out, out, out_pitch, st);
-    case 1024: return launch_istft<1024>(spec, B, T, C_in, C_out, hop, win, tw, tail_in, tail_out, out, out_pitch, st);
-    case 2048: return launch_istft<2048>(spec, B, T, C_in, C_out, hop, win, tw, tail_in, tail_out, out, out_pitch, st);
+    case 256: return launch_istft<256>(spec, B, T, C_in, C_out, hop, win, tw, tail_in, tail_out, out, out_pitch, out_rows, st);
+    case 512: return launch_istft<512>(spec, B, T, C_in, C_out, hop, win, tw, tail_in, tail_out, out, out_pitch, out_rows, st);
+    case 1024: return launch_istft<1024>(spec, B, T, C_in, C_out, hop, win, tw, tail_in, tail_out, out, out_pitch, out_rows, st);
+    case 2048: return launch_istft<2048>(spec, B, T, C_in, C_out, hop, win, tw, tail_in, tail_out, out, out_pitch, out_rows, st);
   }
   return mcag_set_error(1, "istft: frame size must be 256, 512, 1024 or 2048");
 }

@@ -138,7 +138,8 @@ class Processor:
 
 
 class _Localiser(Processor):
-    def __init__(self, kind, sampleRate, mic_xyz, numOfSources, usePowerFloor, n_streams, max_frames_per_call, frame_size=None, emit=0):
+    def __init__(self, kind, sampleRate, mic_xyz, numOfSources, usePowerFloor, n_streams, max_frames_per_call, frame_size=None, emit=0,
+                 srp_form=0):
         mic_xyz = np.ascontiguousarray(mic_xyz, dtype=np.float64).reshape(-1, 3)
         self.doa_step = np.float32(5 * np.pi / 180)                         # SteeringBeamforming.cpp:39
         N = frame_size or capi.frame_size(sampleRate, 0.025)                # _frameRate, SourceSeparationAndLocalisation.h:60
@@ -146,7 +147,7 @@ class _Localiser(Processor):
         turns = capi.steer_turns_reference(mic_xyz, sampleRate, N, self.doa_step)
         super().__init__(kind=kind, sample_rate=sampleRate, frame_size=N, hop=N // 2, n_channels=len(mic_xyz), n_streams=n_streams,
                          max_frames_per_call=max_frames_per_call, n_dirs=tau.shape[1], pair_tau=tau, steer_turns=turns,
-                         n_sources=numOfSources, use_power_floor=int(usePowerFloor), noise_margin_db=3.0, emit=emit)
+                         n_sources=numOfSources, use_power_floor=int(usePowerFloor), noise_margin_db=3.0, emit=emit, srp_form=srp_form)
         self._callback = None
 
     def setCallback(self, cb):

@@ -34,6 +34,15 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ssl_mcbeam_48k.npz"), fs=fs, xyz=xyz, S=1, x=x.astype(np.int16), chunk=1024,
                         out=r["out"][:1], doa_deg=r["doa_deg"], prob=r["prob"], power=r["power"], energy=r["energy"],
                         fired_frame=r["fired_frame"], N=r["N"])
+    # 2b. BASELINE config 5 geometry: 16-mic linear array, 0.035 m pitch, 16 kHz (the shape whose pair sum the GPU build runs in channel
+    #     form on the tensor cores); two sources asked, two present
+    fs = 16000
+    xyz = scenes.linear_array((np.arange(16) - 7.5) * 0.035)
+    x = np.round(scenes.far_field_scene(xyz, fs, 512 + 47 * 256 + 100, scenes.azimuth_dirs([np.deg2rad(-35), np.deg2rad(50)]), seed=104))
+    r = orc.ssl_run(fs, xyz, 2, x, chunk=3000, prefix="ref")
+    np.savez_compressed(os.path.join(HERE, "ssl_lin16_16k.npz"), fs=fs, xyz=xyz, S=2, x=x.astype(np.int16), chunk=3000,
+                        out=r["out"][:2].astype(np.float32), doa_deg=r["doa_deg"], prob=r["prob"], power=r["power"], energy=r["energy"],
+                        fired_frame=r["fired_frame"], N=r["N"])
     # 3. FreqGCCBinauralLocalisation, 0.086 m (test_mcarray.cpp:284)
     fs = 16000
     xyz = scenes.linear_array([0, 0.086])

@@ -129,6 +129,50 @@ def test_ssl_against_reference_golden(mb, name):
     assert np.all(out[S:] == 0)
 
 
+@pytest.mark.parametrize("form", ["pair", "channel"])
+def test_ssl_16mic_against_reference_golden(mb, form):
+    """BASELINE config 5 geometry (16-mic linear array, two sources) against the reference's own code: the pair form
+    (gcc_tau_kernel, pair by pair like SteeringBeamforming::computeCorrelations) and the channel form on the tensor cores
+    (srp_tc_kernel, what the processor picks by default for 16/32/48/64 channels) must both give the reference's DOA cells
+    bit-exact and its energy map / prob / separated audio within tolerance."""
+    g = np.load(os.path.join(G, "ssl_lin16_16k.npz"))
+    fs, S, xyz = int(g["fs"]), int(g["S"]), g["xyz"]
+    x = g["x"].astype(np.float32)
+    p = mb.SourceSeparationAndLocalisation(fs, xyz, S, usePowerFloor=False, max_frames_per_call=64, srp_form={"pair": 1, "channel": 2}[form])
+    assert p.info.srp_form == {"pair": 1, "channel": 2}[form]
+    auto = mb.SourceSeparationAndLocalisation(fs, xyz, S, usePowerFloor=False, max_frames_per_call=64)
+    assert auto.info.srp_form == 2                                         # the default for this shape is the tensor-core path
+    auto.close()
+    outs, cells, energy, prob = [], [], [], []
+    chunk = int(g["chunk"])
+    for pos in range(0, x.shape[1], chunk):
+        outs.append(p.process(x[:, pos:pos + chunk]))
+        if p.frames_done:
+            cells.append(p.cells()[0]); energy.append(p.energy()[0]); prob.append(p.prob()[0])
+    out = np.concatenate(outs, axis=1); cells = np.concatenate(cells); energy = np.concatenate(energy); prob = np.concatenate(prob)
+    step = np.float32(5 * np.pi / 180)
+    ref_cells = np.round((g["doa_deg"] * np.pi / 180 + np.pi / 2) / step).astype(np.int32)
+    assert cells.shape == ref_cells.shape
+    assert np.array_equal(cells, ref_cells), f"{np.sum(cells != ref_cells)} DOA cells differ ({form} form)"
+    assert_close(energy, g["energy"], (1,), f"energy map ({form} form)")
+    assert_close(prob, g["prob"], (1,), "prob")
+    ref = g["out"]
+    assert out.shape[1] == ref.shape[1]
+    assert_close(out[:S].T.reshape(-1, p.info.hop, S), ref.T.reshape(-1, p.info.hop, S), (1, 2), "separated audio")
+    assert np.all(out[S:] == 0)
+
+
+def test_ssl_channel_form_needs_consistent_delays(mb):
+    """the reference's scalar pair distances (SteeringBeamforming.cpp:67-73) only factor into per-microphone delays for linear
+    arrays in monotonic order: a planar array keeps the pair form by default and refuses srp_form = channel."""
+    from mcarray_b200 import capi
+    xyz = scenes.planar_array(4, 4, 0.035)
+    p = mb.SourceSeparationAndLocalisation(16000, xyz, 1, usePowerFloor=False, max_frames_per_call=8)
+    assert p.info.srp_form == 1
+    with pytest.raises(capi.McagError):
+        mb.SourceSeparationAndLocalisation(16000, xyz, 1, usePowerFloor=False, max_frames_per_call=8, srp_form=2)
+
+
 def test_ssl_power_floor_gate(mb, orc):
     fs = 16000
     xyz = scenes.linear_array([0, 0.07, 0.175, 0.21])
