@@ -8,6 +8,8 @@
 #include "fft.cuh"
 #include "kernels.h"
 
+#include <type_traits>
+
 namespace mcag {
 
 // ---------------------------------------------------------------------------------------------------
@@ -35,13 +37,27 @@ __device__ __forceinline__ void pair_table(unsigned char *s_pair, int M, int P, 
   }
 }
 
-// all P pairs of the frame whose whitened spectra are in s_U; every thread of the CTA calls it (uniform trip count)
+// E/O twiddles conj(W_N^k) of the packed inverse real transform for the 8 bins k = j + r*TPF this thread builds: the same for
+// every pair and frame, so they live in registers
+template <int N> __device__ __forceinline__ void load_eo_twiddles(const float2 *s_tw, int j, float2 (&wk)[8]) {
+  constexpr int NC = N / 2, TPF = NC / 8;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) wk[r] = tw_lookup<true>(s_tw, j + r * TPF, NC);
+}
+
+// all P pairs of the frame whose whitened spectra are in s_U; every thread of the CTA calls it (uniform trip count).
+// The lag window only needs the lowest and highest NC/R_last outputs of the inverse transform, so its last pass is
+// output-pruned (fft_inv_last_pruned): nothing is stored, the window values go from registers into the arg-max.
 template <int N, int G>
-__device__ __forceinline__ void tdoa_pairs(const float2 *s_U, const float2 *s_tw, const float2 *s_twp, float2 *buf, float *curve,
-                                           const unsigned char *s_pair, float *s_bv, int *s_bi, int P, int max_lag, int g, int j,
-                                           float *__restrict__ curves_ft, int32_t *__restrict__ lags_ft, float *__restrict__ peaks_ft) {
+__device__ __forceinline__ void tdoa_pairs(const float2 *s_U, const float2 (&wk)[8], const float2 *s_twp, fft_buf_t buf, const unsigned char *s_pair,
+                                           float *s_bv, int *s_bi, int P, int max_lag, int g, int j, float *__restrict__ curves_ft,
+                                           int32_t *__restrict__ lags_ft, float *__restrict__ peaks_ft) {
   constexpr int NC = N / 2, TPF = NC / 8, KP = spec_pitch(N);
+  using PL = FftPlan<NC>;
+  constexpr int RL = PL::R[PL::NP - 1], NBL = 8 / RL, NSL = NC / RL;
   const int L = 2 * max_lag + 1;
+  const int hl = max_lag >> 1, hh = (max_lag + 1) >> 1;   // complex outputs 0..hl hold lags >= 0, NC-hh..NC-1 the negative ones
+  const bool pruned = hl < NSL && hh <= NSL;
   const int rounds = (P + G - 1) / G;
   for (int it = 0; it < rounds; ++it) {   // every thread runs every round, stores are predicated
     const int p = it * G + g;
@@ -56,32 +72,64 @@ __device__ __forceinline__ void tdoa_pairs(const float2 *s_U, const float2 *s_tw
       if (k == 0) { gk.y = 0.f; gn.y = 0.f; }
       float2 e = make_float2(0.5f * (gk.x + gn.x), 0.5f * (gk.y - gn.y));
       float2 d = make_float2(0.5f * (gk.x - gn.x), 0.5f * (gk.y + gn.y));
-      float2 o = cmul(d, tw_lookup<true>(s_tw, k, NC));
+      float2 o = cmul(d, wk[r]);
       v[r] = make_float2(e.x - o.y, e.y + o.x);
     }
-    fft_run<NC, true>(v, buf, s_twp, j, g);
     const float g0 = Ui[0].x * Uj[0].x, gny = Ui[NC].x * Uj[NC].x;   // both spectra are real at DC / Nyquist
+    const float b_even = 0.5f * (g0 + gny), b_odd = 0.5f * (g0 - gny);
+    float *cdst = (curves_ft && live) ? curves_ft + (size_t)p * L : nullptr;
     float best = -3.0e38f; int besti = 0x7fffffff;
-    for (int c = j; c < L; c += TPF) {
-      const int l = c - max_lag;
-      const int li = (l + N) & (N - 1);
-      const float2 z = buf[fft_pad(li >> 1)];
-      const float s = ((li & 1) ? z.y : z.x) + 0.5f * (g0 + ((l & 1) ? -gny : gny));
-      curve[c] = s;
-      if (s > best) { best = s; besti = c; }   // ascending c per thread: first maximum kept
+    auto cand = [&](int l, float val) {   // first maximum: the lowest window index wins ties
+      const float sv = val + ((l & 1) ? b_odd : b_even);
+      const int c = l + max_lag;
+      if (cdst) cdst[c] = sv;
+      if (sv > best || (sv == best && c < besti)) { best = sv; besti = c; }
+    };
+    if (pruned) {
+      fft_run_head<NC, true>(v, buf, s_twp, j, g);
+      auto block = [&](auto bc) {
+        constexpr int B_ = decltype(bc)::value;
+        const int jj = j + B_ * (NC / 8);
+        const bool lo = jj <= hl, hi = jj >= NSL - hh;
+        if (lo || hi) {
+          float2 y0, y1;
+          fft_inv_last_pruned<NC, B_>(buf, s_twp, j, lo, hi, y0, y1);
+          if (lo) {
+            cand(2 * jj, y0.x);
+            if (2 * jj + 1 <= max_lag) cand(2 * jj + 1, y0.y);
+          }
+          if (hi) {
+            const int l = 2 * (jj + (RL - 1) * NSL) - N;   // <= -2
+            if (l >= -max_lag) cand(l, y1.x);
+            cand(l + 1, y1.y);
+          }
+        }
+      };
+      block(std::integral_constant<int, 0>{});
+      if constexpr (NBL > 1) block(std::integral_constant<int, 1>{});
+      if constexpr (NBL > 2) { block(std::integral_constant<int, 2>{}); block(std::integral_constant<int, 3>{}); }
+    } else {
+      fft_run<NC, true>(v, buf, s_twp, j, g);
+      for (int c = j; c < L; c += TPF) {
+        const int l = c - max_lag;
+        const int li = (l + N) & (N - 1);
+        const float2 z = fft_buf_get(buf, li >> 1);
+        cand(l, (li & 1) ? z.y : z.x);
+      }
     }
     // first-maximum argmax across the group
     if constexpr (TPF >= 32) {
       warp_argmax(best, besti);
       constexpr int WPF = TPF / 32;
       if ((threadIdx.x & 31) == 0) { s_bv[g * WPF + (j >> 5)] = best; s_bi[g * WPF + (j >> 5)] = besti; }
-      group_sync<TPF>(g);
+      group_sync<TPF>(g);   // also: every thread of the group is done reading buf
       if (j == 0 && live) {
         float bv = s_bv[g * WPF]; int bi = s_bi[g * WPF];
         for (int w = 1; w < WPF; ++w) { float ov = s_bv[g * WPF + w]; int oi = s_bi[g * WPF + w]; if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; } }
         lags_ft[p] = bi - max_lag;
         if (peaks_ft) peaks_ft[p] = bv;
       }
+      group_sync<TPF>(g);   // s_bv / s_bi are rewritten by the next round
     } else {
       const unsigned gmask = ((1u << (TPF & 31)) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(TPF - 1));
 #pragma unroll
@@ -96,11 +144,6 @@ __device__ __forceinline__ void tdoa_pairs(const float2 *s_U, const float2 *s_tw
       }
       group_sync<TPF>(g);
     }
-    if (curves_ft && live) {
-      float *dst = curves_ft + (size_t)p * L;
-      for (int c = j; c < L; c += TPF) dst[c] = curve[c];
-    }
-    group_sync<TPF>(g);
   }
 }
 
@@ -111,12 +154,12 @@ __global__ void __launch_bounds__(G *(N / 16)) tdoa_kernel(const float2 *__restr
   constexpr int NC = N / 2, TPF = NC / 8, KP = spec_pitch(N), NT = G * TPF, WPF = (TPF + 31) / 32;
   const int P = M * (M - 1) / 2, L = 2 * max_lag + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2 *s_U = reinterpret_cast<float2 *>(smem_raw);                 // M * KP
+  unsigned char *smem = fft_align_smem(smem_raw, 8 * NC);
+  float2 *s_buf = reinterpret_cast<float2 *>(smem);                   // G * fft_buf_len(NC), each buffer aligned to its size
+  float2 *s_U = s_buf + G * fft_buf_len(NC);                          // M * KP
   float2 *s_tw = s_U + (size_t)M * KP;                                // fft_table_len(N): tw[NC] then twp
   float2 *s_twp = s_tw + NC;
-  float2 *s_buf = s_tw + fft_table_len(N);                            // G * fft_buf_len(NC)
-  float *s_curve = reinterpret_cast<float *>(s_buf + G * fft_buf_len(NC));   // G * L
-  float *s_bv = s_curve + G * L;                                      // G * WPF
+  float *s_bv = reinterpret_cast<float *>(s_tw + fft_table_len(N));   // G * WPF
   int *s_bi = reinterpret_cast<int *>(s_bv + G * WPF);                // G * WPF
   unsigned char *s_pair = reinterpret_cast<unsigned char *>(s_bi + G * WPF);   // 2 * P
 
@@ -131,7 +174,9 @@ __global__ void __launch_bounds__(G *(N / 16)) tdoa_kernel(const float2 *__restr
   __syncthreads();
   const int g = tid / TPF, j = tid % TPF;
   const long long ft = (long long)b * T + t;
-  tdoa_pairs<N, G>(s_U, s_tw, s_twp, s_buf + g * fft_buf_len(NC), s_curve + g * L, s_pair, s_bv, s_bi, P, max_lag, g, j,
+  float2 wk[8];
+  load_eo_twiddles<N>(s_tw, j, wk);
+  tdoa_pairs<N, G>(s_U, wk, s_twp, smem_u32(s_buf + g * fft_buf_len(NC)), s_pair, s_bv, s_bi, P, max_lag, g, j,
                    curves ? curves + ft * P * L : nullptr, lags + ft * P, peaks ? peaks + ft * P : nullptr);
 }
 
@@ -142,20 +187,20 @@ __global__ void __launch_bounds__(G *(N / 16)) tdoa_kernel(const float2 *__restr
 //   3. runs the pair phase above.
 // Compulsory HBM traffic per frame: 4*M*hop bytes in, 4*P bytes out (+ 8*M*(N/2+2) when spectra are requested).
 template <int N, int G>
-__global__ void __launch_bounds__(G *(N / 16)) stft_tdoa_kernel(const float *__restrict__ x, long long row_pitch, int B, int T, int M, int hop,
+__global__ void __launch_bounds__(G *(N / 16), 768 / (G * (N / 16))) stft_tdoa_kernel(const float *__restrict__ x, long long row_pitch, int B, int T, int M, int hop,
                                                                  int max_lag, const float *__restrict__ win, const float2 *__restrict__ tw_g,
                                                                  float2 *__restrict__ spec, float *__restrict__ chan_pow,
                                                                  float *__restrict__ curves, int32_t *__restrict__ lags) {
   constexpr int NC = N / 2, TPF = NC / 8, KP = spec_pitch(N), NT = G * TPF, WPF = (TPF + 31) / 32;
   const int P = M * (M - 1) / 2, L = 2 * max_lag + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2 *s_U = reinterpret_cast<float2 *>(smem_raw);                 // M * KP
+  unsigned char *smem = fft_align_smem(smem_raw, 8 * NC);
+  float2 *s_buf = reinterpret_cast<float2 *>(smem);                   // G * NC, each buffer aligned to its size
+  float2 *s_U = s_buf + G * fft_buf_len(NC);                          // M * KP
   float2 *s_tw = s_U + (size_t)M * KP;                                // fft_table_len(N)
   float2 *s_twp = s_tw + NC;
-  float2 *s_buf = s_tw + fft_table_len(N);                            // G * NC
-  float2 *s_w = s_buf + G * fft_buf_len(NC);                          // NC (window, pairs of samples)
-  float *s_curve = reinterpret_cast<float *>(s_w + NC);               // G * L
-  float *s_bv = s_curve + G * L;                                      // G * WPF
+  float2 *s_w = s_tw + fft_table_len(N);                              // NC (window, pairs of samples)
+  float *s_bv = reinterpret_cast<float *>(s_w + NC);                  // G * WPF
   int *s_bi = reinterpret_cast<int *>(s_bv + G * WPF);                // G * WPF
   unsigned char *s_pair = reinterpret_cast<unsigned char *>(s_bi + G * WPF);   // 2 * P
 
@@ -165,7 +210,9 @@ __global__ void __launch_bounds__(G *(N / 16)) stft_tdoa_kernel(const float *__r
   pair_table<N, G>(s_pair, M, P, tid, NT);
   __syncthreads();
   const int g = tid / TPF, j = tid % TPF;
-  float2 *buf = s_buf + g * fft_buf_len(NC);
+  const fft_buf_t buf = smem_u32(s_buf + g * fft_buf_len(NC));
+  float2 wk[8];
+  load_eo_twiddles<N>(s_tw, j, wk);
   const bool vec_ok = ((row_pitch & 1) == 0) && ((hop & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
   const long long nframes = (long long)B * T;
 
@@ -191,7 +238,7 @@ __global__ void __launch_bounds__(G *(N / 16)) stft_tdoa_kernel(const float *__r
       float2 *out = spec ? spec + ((ft * M + m) * KP) : nullptr;
       float pw = 0.f;
       for (int k = j; k <= NC / 2; k += TPF) {
-        float2 zk = buf[fft_pad(k)], zn = buf[fft_pad((NC - k) & (NC - 1))];
+        float2 zk = fft_buf_get(buf, k), zn = fft_buf_get(buf, (NC - k) & (NC - 1));
         float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
         float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));   // -i/2 (zk - conj zn)
         float2 w = tw_lookup<false>(s_tw, k, NC);
@@ -227,7 +274,7 @@ __global__ void __launch_bounds__(G *(N / 16)) stft_tdoa_kernel(const float *__r
       group_sync<TPF>(g);
     }
     __syncthreads();
-    tdoa_pairs<N, G>(s_U, s_tw, s_twp, buf, s_curve + g * L, s_pair, s_bv, s_bi, P, max_lag, g, j,
+    tdoa_pairs<N, G>(s_U, wk, s_twp, buf, s_pair, s_bv, s_bi, P, max_lag, g, j,
                      curves ? curves + ft * P * L : nullptr, lags + ft * P, nullptr);
     __syncthreads();
   }
@@ -238,8 +285,8 @@ template <int N> static int launch_tdoa(const float2 *spec, int B, int T, int M,
   constexpr int NC = N / 2, TPF = NC / 8;
   constexpr int G = (TPF >= 128) ? 2 : (256 / TPF);
   const int P = M * (M - 1) / 2, L = 2 * max_lag + 1;
-  size_t smem = sizeof(float2) * ((size_t)M * spec_pitch(N) + fft_table_len(N) + (size_t)G * fft_buf_len(NC)) + sizeof(float) * G * L +
-                8 * G * ((TPF + 31) / 32) + 2 * P + 16;
+  size_t smem = sizeof(float2) * ((size_t)M * spec_pitch(N) + fft_table_len(N) + (size_t)G * fft_buf_len(NC)) +
+                8 * G * ((TPF + 31) / 32) + 2 * P + 16 + 8 * NC /* buffer alignment slack */;
   if (smem > 220 * 1024) return mcag_set_error(1, "tdoa: M*N too large for the shared-memory staged kernel");
   auto kern = tdoa_kernel<N, G>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -253,8 +300,8 @@ template <int N> static int launch_stft_tdoa(const float *x, long long row_pitch
   constexpr int NC = N / 2, TPF = NC / 8;
   constexpr int G = (TPF >= 128) ? 4 : (256 / TPF);
   const int P = M * (M - 1) / 2, L = 2 * max_lag + 1;
-  size_t smem = sizeof(float2) * ((size_t)M * spec_pitch(N) + fft_table_len(N) + (size_t)G * fft_buf_len(NC) + NC) + sizeof(float) * G * L +
-                8 * G * ((TPF + 31) / 32) + 2 * P + 16;
+  size_t smem = sizeof(float2) * ((size_t)M * spec_pitch(N) + fft_table_len(N) + (size_t)G * fft_buf_len(NC) + NC) +
+                8 * G * ((TPF + 31) / 32) + 2 * P + 16 + 8 * NC /* buffer alignment slack */;
   if (smem > 220 * 1024) return mcag_set_error(1, "tdoa: M*N too large for the shared-memory staged kernel");
   auto kern = stft_tdoa_kernel<N, G>;
   static int sm_count = 0, dev_cached = -1;

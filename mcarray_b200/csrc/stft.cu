@@ -19,12 +19,13 @@ __global__ void __launch_bounds__(G *(N / 16)) stft_kernel(const float *__restri
                                                             float2 *__restrict__ spec, float *__restrict__ chan_pow) {
   constexpr int NC = N / 2, TPF = NC / 8, KP = spec_pitch(N), NT = G * TPF;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float *s_x = reinterpret_cast<float *>(smem_raw);                   // (F-1)*hop_max + N floats, hop <= N
+  unsigned char *smem = fft_align_smem(smem_raw, 8 * NC);
+  float2 *s_buf = reinterpret_cast<float2 *>(smem);                   // G * fft_buf_len(NC), each buffer aligned to its size
+  float *s_x = reinterpret_cast<float *>(s_buf + G * fft_buf_len(NC));   // (F-1)*hop_max + N floats, hop <= N
   float *s_w = s_x + ((F - 1) * N + N);                               // N
   float2 *s_tw = reinterpret_cast<float2 *>(s_w + N);                 // fft_table_len(N): tw[NC] then twp
   float2 *s_twp = s_tw + NC;                                          // per-thread inter-pass twiddles
-  float2 *s_buf = s_tw + fft_table_len(N);                            // G * fft_buf_len(NC)
-  float *s_red = reinterpret_cast<float *>(s_buf + G * fft_buf_len(NC));   // G * (TPF/32 or 1)
+  float *s_red = reinterpret_cast<float *>(s_tw + fft_table_len(N));  // G * (TPF/32 or 1)
   __shared__ __align__(8) uint64_t s_bar;
 
   const int tid = threadIdx.x, row = blockIdx.y, t0 = blockIdx.x * F;
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(G *(N / 16)) stft_kernel(const float *__restri
   __syncthreads();
 
   const int g = tid / TPF, j = tid % TPF;
-  float2 *buf = s_buf + g * fft_buf_len(NC);
+  const fft_buf_t buf = smem_u32(s_buf + g * fft_buf_len(NC));
   const int b = row / M, m = row % M;
 
   for (int f = g; f < F; f += G) {   // uniform trip count per group; inactive frames are skipped as a group
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(G *(N / 16)) stft_kernel(const float *__restri
       float2 *out = spec + (((long long)b * T + (t0 + f)) * M + m) * KP;
       float pw = 0.f;
       for (int k = j; k <= NC / 2; k += TPF) {
-        float2 zk = buf[fft_pad(k)], zn = buf[fft_pad((NC - k) & (NC - 1))];
+        float2 zk = fft_buf_get(buf, k), zn = fft_buf_get(buf, (NC - k) & (NC - 1));
         float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
         float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));   // -i/2 (zk - conj zn)
         float2 w = tw_lookup<false>(s_tw, k, NC);
@@ -130,12 +131,13 @@ __global__ void __launch_bounds__(G *(N / 16)) istft_kernel(const float2 *__rest
   constexpr int NC = N / 2, TPF = NC / 8, KP = spec_pitch(N), NT = G * TPF;
   const int R = N / hop;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float *s_y = reinterpret_cast<float *>(smem_raw);                   // (F + Rmax - 1) * N, Rmax = 4
+  unsigned char *smem = fft_align_smem(smem_raw, 8 * NC);
+  float2 *s_buf = reinterpret_cast<float2 *>(smem);                   // G * fft_buf_len(NC), each buffer aligned to its size
+  float *s_y = reinterpret_cast<float *>(s_buf + G * fft_buf_len(NC));   // (F + Rmax - 1) * N, Rmax = 4
   float *s_w = s_y + (F + 3) * N;                                     // N
   float2 *s_tw = reinterpret_cast<float2 *>(s_w + N);                 // fft_table_len(N): tw[NC] then twp
   float2 *s_twp = s_tw + NC;                                          // per-thread inter-pass twiddles
-  float2 *s_buf = s_tw + fft_table_len(N);                            // G * fft_buf_len(NC)
-  float2 *s_in = s_buf + G * fft_buf_len(NC);                         // G * KP  (staged spectrum rows)
+  float2 *s_in = s_tw + fft_table_len(N);                             // G * KP  (staged spectrum rows)
 
   const int tid = threadIdx.x, row = blockIdx.y, seg0 = blockIdx.x * F;
   const int b = row / C_out, c = row % C_out;
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(G *(N / 16)) istft_kernel(const float2 *__rest
   __syncthreads();
 
   const int g = tid / TPF, j = tid % TPF;
-  float2 *buf = s_buf + g * fft_buf_len(NC);
+  const fft_buf_t buf = smem_u32(s_buf + g * fft_buf_len(NC));
   float2 *xin = s_in + g * KP;
   for (int fi = g; fi < nfr; fi += G) {
     const int t = seg0 - (R - 1) + fi;
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(G *(N / 16)) istft_kernel(const float2 *__rest
       fft_run<NC, true>(v, buf, s_twp, j, g);
       const float sc = 1.0f / (float)NC;
       for (int n = j; n < NC; n += TPF) {
-        float2 z = buf[fft_pad(n)];
+        float2 z = fft_buf_get(buf, n);
         y[2 * n] = z.x * sc * s_w[2 * n];
         y[2 * n + 1] = z.y * sc * s_w[2 * n + 1];
       }
@@ -197,7 +199,7 @@ template <int N> static int launch_stft(const float *x, long long row_pitch, int
   constexpr int G = (TPF >= 128) ? 2 : (256 / TPF);
   constexpr int F = G > 8 ? G : 8;
   size_t smem = sizeof(float) * ((F - 1) * N + N) + sizeof(float) * N + sizeof(float2) * fft_table_len(N) + sizeof(float2) * G * fft_buf_len(NC) +
-                sizeof(float) * G * 4;
+                sizeof(float) * G * 4 + 8 * NC /* buffer alignment slack */;
   auto kern = stft_kernel<N, F, G>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((T + F - 1) / F, rows);
@@ -218,7 +220,7 @@ template <int N> static int launch_istft(const float2 *spec, int B, int T, int C
   constexpr int F = 8;
   constexpr int G = (TPF >= 128) ? 2 : (256 / TPF);
   size_t smem = sizeof(float) * (F + 3) * N + sizeof(float) * N + sizeof(float2) * fft_table_len(N) + sizeof(float2) * G * fft_buf_len(NC) +
-                sizeof(float2) * G * spec_pitch(N);
+                sizeof(float2) * G * spec_pitch(N) + 8 * NC /* buffer alignment slack */;
   auto kern = istft_kernel<N, F, G>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int R = N / hop;
