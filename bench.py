@@ -216,7 +216,124 @@ class Cfg4Sharded(Cfg4):
         return None
 
 
-WORKLOADS = {"cfg2": Cfg2, "cfg4": Cfg4, "cfg4s": Cfg4Sharded, "cfg5": Cfg5}
+def _threaded(fn, items, n_threads):
+    res = [None] * len(items)
+
+    def work(i0, i1):
+        for i in range(i0, i1):
+            res[i] = fn(items[i])
+    th = [threading.Thread(target=work, args=(len(items) * i // n_threads, len(items) * (i + 1) // n_threads)) for i in range(n_threads)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    return res
+
+
+class Cfg1Mask(Workload):
+    """BASELINE.json configs[0], masking half: FastBinauralMasking (45 mel bands, RELATIVE / BOTH) on 16 kHz stereo, 512-sample frames."""
+    name = "cfg1m: 2-channel FastBinauralMasking (45 mel bands 500-5000 Hz, RELATIVE, BOTH), 0.086 m, 16 kHz, N=512, hop=256"
+    fs, N, hop, M, d = 16000, 512, 256, 2, 0.086
+    B_default, T_default = 2048, 125
+    cpu_frames = (128, 512)
+
+    def scene(self, stream_id, n):
+        from mcarray_b200 import scenes
+        az = [0.0, np.deg2rad(30 + 10 * (stream_id % 5))]
+        return scenes.far_field_scene(scenes.linear_array([0, self.d]), self.fs, n, scenes.azimuth_dirs(az), seed=scenes.stream_seed(stream_id))
+
+    def make(self, mb, B, T):
+        return mb.FastBinauralMasking(self.fs, self.d, 500, 5000, "RELATIVE", "BOTH", n_streams=B, max_frames_per_call=T, frame_size=self.N)
+
+    def result_bytes(self, p, B, T):
+        return B * 2 * T * self.hop * 4
+
+    def fetch_result(self, p):
+        return None
+
+    def kernel_bytes_per_frame(self):
+        K, hop, nb = self.N // 2 + 1, self.hop, 45
+        return {"stft": 4 * 2 * hop + 8 * 2 * K, "mask_stats": 8 * 2 * K + 4 * 6 * nb, "mask_scan": 4 * 6 * nb + 4 * 2 * nb, "mask_apply": 2 * 8 * 2 * K + 4 * 2 * nb,
+                "istft": 8 * 2 * K + 4 * 2 * hop}
+
+    def pipeline_bytes_per_frame(self):
+        return 4 * 2 * self.hop + 4 * 2 * self.hop                    # SURVEY.md 8d: samples in, samples out
+
+    def cpu_run(self, orc, x64, n_threads):
+        return _threaded(lambda x: orc.mask_run(self.fs, self.d, 500, 5000, 1, 0, x)["out"], list(x64), n_threads)
+
+
+class Cfg1Loc(Workload):
+    """BASELINE.json configs[0], localisation half: FreqGCCBinauralLocalisation (61-cell GCC-PHAT curve, 0.8 smoothing, arg-max)."""
+    name = "cfg1l: 2-channel FreqGCCBinauralLocalisation (61 delays, 3 degree grid), 0.086 m, 16 kHz, N=512, hop=256"
+    fs, N, hop, M, d = 16000, 512, 256, 2, 0.086
+    B_default, T_default = 2048, 125
+    cpu_frames = (128, 512)
+
+    def scene(self, stream_id, n):
+        from mcarray_b200 import scenes
+        az = [np.deg2rad(-60 + 7 * (stream_id % 17))]
+        return scenes.far_field_scene(scenes.linear_array([0, self.d]), self.fs, n, scenes.azimuth_dirs(az), seed=scenes.stream_seed(stream_id))
+
+    def make(self, mb, B, T):
+        return mb.FreqGCCBinauralLocalisation(self.fs, self.d, usePowerFloor=False, n_streams=B, max_frames_per_call=T, frame_size=self.N)
+
+    def result_bytes(self, p, B, T):
+        return B * T * 4
+
+    def fetch_result(self, p):
+        return p.cells()
+
+    def kernel_bytes_per_frame(self):
+        K, hop, D = self.N // 2 + 1, self.hop, 61
+        return {"stft": 4 * 2 * hop + 8 * 2 * K, "gcc_tau": 8 * 2 * K + 4 * D, "curve_scan": 2 * 4 * D + 4}
+
+    def pipeline_bytes_per_frame(self):
+        return 4 * 2 * self.hop + 4                                   # samples in, arg-max cell out
+
+    def cpu_run(self, orc, x64, n_threads):
+        return _threaded(lambda x: orc.freqgcc_run(self.fs, self.d, x)["idx"], list(x64), n_threads)
+
+
+class Cfg3(Workload):
+    """32-mic linear array delay-and-sum beamformer steered to 181 azimuths, 2048-sample frames (BASELINE.json configs[2])."""
+    name = "cfg3: 32-mic linear array 0.04 m pitch, delay-and-sum to 181 azimuths (spectra out), 48 kHz, N=2048, hop=1024"
+    fs, N, hop, M, D = 48000, 2048, 1024, 32, 181
+    B_default, T_default = 8, 64
+    cpu_frames, cpu_streams = (8, 16), 16
+
+    def xyz(self):
+        from mcarray_b200 import scenes
+        return scenes.linear_array((np.arange(self.M) - (self.M - 1) / 2) * 0.04)
+
+    def doas(self):
+        return np.deg2rad(np.arange(-90, 91, 1.0))
+
+    def scene(self, stream_id, n):
+        from mcarray_b200 import scenes
+        az = np.deg2rad(-75 + 11 * (stream_id % 14))
+        return scenes.far_field_scene(self.xyz(), self.fs, n, scenes.azimuth_dirs([az]), seed=scenes.stream_seed(stream_id))
+
+    def make(self, mb, B, T):
+        return mb.DelayAndSumFan(self.fs, self.xyz(), self.N, self.doas(), n_streams=B, max_frames_per_call=T)
+
+    def result_bytes(self, p, B, T):
+        return B * T * self.D * p.info.spectrum_pitch * 8
+
+    def fetch_result(self, p):
+        return p.fetch(9, (p.info.n_streams, p.frames_done, self.D, p.info.spectrum_pitch))   # MCAG_OUT_BEAMS
+
+    def kernel_bytes_per_frame(self):
+        M, hop, K, D = self.M, self.hop, self.N // 2 + 1, self.D
+        return {"stft": 4 * M * hop + 8 * M * K, "ds_fan": 8 * M * K + 8 * D * K}
+
+    def pipeline_bytes_per_frame(self):
+        return 4 * self.M * self.hop + 8 * self.D * (self.N // 2 + 1)  # SURVEY.md 8d: 1.62 MB / frame
+
+    def cpu_run(self, orc, x64, n_threads):
+        xs = self.xyz()[:, 0]
+        return _threaded(lambda x: orc.ds_fan(orc.stft(x, self.N, self.hop), self.N, self.fs, xs, self.doas()).shape, list(x64), n_threads)
+
+
+WORKLOADS = {"cfg1m": Cfg1Mask, "cfg1l": Cfg1Loc, "cfg2": Cfg2, "cfg3": Cfg3, "cfg4": Cfg4, "cfg4s": Cfg4Sharded, "cfg5": Cfg5}
 
 
 # ----------------------------------------------------------------------------------------------------------------------

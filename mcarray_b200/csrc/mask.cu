@@ -10,38 +10,52 @@ namespace mcag {
 
 constexpr int MS_NSTAT = 6;   // pw2, num, eL, eR, pL, pR
 
-// one CTA per frame.  stats[bt][b][0] = sum_{k<N/2} H2 |(L+R)/2|^2      (getFramePower :496-538)
+// The mel bands are narrow (a triangular filter covers a few per cent of the bins), so every kernel first finds the non-zero bin
+// range of each band (and the band range of each bin) from the coefficient table; the frame loops then touch only those.
+//
+// Persistent CTAs, one warp per frame at a time.  stats[bt][b][0] = sum_{k<N/2} H2 |(L+R)/2|^2      (getFramePower :496-538)
 //                               [1] = sum_{k<K}   H2 Re(R conj L)        (normaliseFFTCorrelation :437-441)
 //                               [2],[3] = sum_{k<K} H2 |L|^2, |R|^2      (:446-452, maskFrameByScaling :262-264)
 //                               [4],[5] = sum_{k<N/2} H2 |L|^2, |R|^2    (noisyFrame -> getPower :222,520-538)
-__global__ void __launch_bounds__(256) mask_stats_kernel(const float2 *__restrict__ spec, int N, const float *__restrict__ H2, int nb,
-                                                          float *__restrict__ stats) {
-  extern __shared__ float4 s_q[];   // per bin: (|L+R|^2/4, Re(R L*), |L|^2, |R|^2)
+// Each band is summed by one lane in ascending bin order (the reference's order; zero coefficients add exact zeros).
+constexpr int MS_WARPS = 8;
+__global__ void __launch_bounds__(32 * MS_WARPS) mask_stats_kernel(const float2 *__restrict__ spec, long long BT, int N, const float *__restrict__ H2,
+                                                                   int nb, float *__restrict__ stats) {
+  extern __shared__ float4 s_q_all[];   // [MS_WARPS][K] per bin: (|L+R|^2/4, Re(R L*), |L|^2, |R|^2), then the band ranges
   const int KP = spec_pitch(N), K = N / 2 + 1, NH = N / 2;
-  const long long bt = blockIdx.x;
-  const float2 *L = spec + bt * 2 * KP, *R = L + KP;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    const float2 l = L[k], r = R[k];
-    const float mx = 0.5f * l.x + 0.5f * r.x, my = 0.5f * l.y + 0.5f * r.y;
-    s_q[k] = make_float4(mx * mx + my * my, r.x * l.x + r.y * l.y, l.x * l.x + l.y * l.y, r.x * r.x + r.y * r.y);
+  int *s_lo = reinterpret_cast<int *>(s_q_all + (size_t)MS_WARPS * K), *s_hi = s_lo + nb;
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+    const float *h = H2 + (size_t)b * KP;
+    int lo = K, hi = 0;
+    for (int k = 0; k < K; ++k)
+      if (h[k] != 0.f) { lo = min(lo, k); hi = k + 1; }
+    s_lo[b] = lo; s_hi[b] = hi;
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  for (int b = warp; b < nb; b += nwarp) {
-    const float *h = H2 + (size_t)b * KP;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 *s_q = s_q_all + (size_t)warp * K;
+  for (long long bt = (long long)blockIdx.x * MS_WARPS + warp; bt < BT; bt += (long long)gridDim.x * MS_WARPS) {
+    const float2 *L = spec + bt * 2 * KP, *R = L + KP;
     for (int k = lane; k < K; k += 32) {
-      const float w = h[k];
-      if (w == 0.f) continue;
-      const float4 q = s_q[k];
-      a1 = fmaf(w, q.y, a1); a2 = fmaf(w, q.z, a2); a3 = fmaf(w, q.w, a3);
-      if (k < NH) { a0 = fmaf(w, q.x, a0); a4 = fmaf(w, q.z, a4); a5 = fmaf(w, q.w, a5); }
+      const float2 l = L[k], r = R[k];
+      const float mx = 0.5f * l.x + 0.5f * r.x, my = 0.5f * l.y + 0.5f * r.y;
+      s_q[k] = make_float4(mx * mx + my * my, r.x * l.x + r.y * l.y, l.x * l.x + l.y * l.y, r.x * r.x + r.y * r.y);
     }
-    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3); a4 = warp_sum(a4); a5 = warp_sum(a5);
-    if (lane == 0) {
+    __syncwarp();
+    for (int b = lane; b < nb; b += 32) {
+      const float *h = H2 + (size_t)b * KP;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f;
+      const int hi = s_hi[b];
+      for (int k = s_lo[b]; k < hi; ++k) {
+        const float w = __ldg(h + k);
+        const float4 q = s_q[k];
+        a1 = fmaf(w, q.y, a1); a2 = fmaf(w, q.z, a2); a3 = fmaf(w, q.w, a3);
+        if (k < NH) { a0 = fmaf(w, q.x, a0); a4 = fmaf(w, q.z, a4); a5 = fmaf(w, q.w, a5); }
+      }
       float *o = stats + (bt * nb + b) * MS_NSTAT;
       o[0] = a0; o[1] = a1; o[2] = a2; o[3] = a3; o[4] = a4; o[5] = a5;
     }
+    __syncwarp();
   }
 }
 
@@ -102,32 +116,54 @@ __global__ void mask_scan_kernel(const float *__restrict__ stats, int B, int T, 
   Qs[i] = Q; noise_s[i] = noise;   // the frame counter (_firstCall) is common to all streams and lives on the host
 }
 
-// one CTA per frame, in place
-__global__ void __launch_bounds__(256) mask_apply_kernel(float2 *__restrict__ spec, int N, const float *__restrict__ H, int nb,
-                                                          const float *__restrict__ gains) {
-  extern __shared__ float s_g[];   // [nb][2]
+// persistent CTAs, one warp per frame at a time, in place; each bin sums only the bands that cover it (in band order)
+__global__ void __launch_bounds__(32 * MS_WARPS) mask_apply_kernel(float2 *__restrict__ spec, long long BT, int N, const float *__restrict__ H, int nb,
+                                                                   const float *__restrict__ gains) {
+  extern __shared__ float s_ga[];   // [MS_WARPS][nb][2] gains, then per bin the band range [blo, bhi)
   const int KP = spec_pitch(N), K = N / 2 + 1, NH = N / 2;
-  const long long bt = blockIdx.x;
-  for (int i = threadIdx.x; i < nb * 2; i += blockDim.x) s_g[i] = gains[bt * nb * 2 + i];
-  __syncthreads();
-  float2 *L = spec + bt * 2 * KP, *R = L + KP;
+  int *s_blo = reinterpret_cast<int *>(s_ga + (size_t)MS_WARPS * nb * 2), *s_bhi = s_blo + K;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    float wl = 0.f, wr = 0.f;
-    for (int b = 0; b < nb; ++b) {
-      const float h = H[(size_t)b * KP + k];
-      wl = fmaf(h, (k < NH) ? s_g[2 * b] : 1.f, wl);
-      wr = fmaf(h, (k < NH) ? s_g[2 * b + 1] : 1.f, wr);
-    }
-    float2 l = L[k], r = R[k];
-    L[k] = make_float2(l.x * wl, l.y * wl);
-    R[k] = make_float2(r.x * wr, r.y * wr);
+    int lo = nb, hi = 0;
+    for (int b = 0; b < nb; ++b)
+      if (H[(size_t)b * KP + k] != 0.f) { lo = min(lo, b); hi = b + 1; }
+    s_blo[k] = lo; s_bhi[k] = hi;
   }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *s_g = s_ga + (size_t)warp * nb * 2;
+  for (long long bt = (long long)blockIdx.x * MS_WARPS + warp; bt < BT; bt += (long long)gridDim.x * MS_WARPS) {
+    for (int i = lane; i < nb * 2; i += 32) s_g[i] = gains[bt * nb * 2 + i];
+    __syncwarp();
+    float2 *L = spec + bt * 2 * KP, *R = L + KP;
+    for (int k = lane; k < K; k += 32) {
+      float wl = 0.f, wr = 0.f;
+      const int bhi = s_bhi[k];
+      for (int b = s_blo[k]; b < bhi; ++b) {
+        const float h = __ldg(H + (size_t)b * KP + k);
+        wl = fmaf(h, (k < NH) ? s_g[2 * b] : 1.f, wl);
+        wr = fmaf(h, (k < NH) ? s_g[2 * b + 1] : 1.f, wr);
+      }
+      float2 l = L[k], r = R[k];
+      L[k] = make_float2(l.x * wl, l.y * wl);
+      R[k] = make_float2(r.x * wr, r.y * wr);
+    }
+    __syncwarp();
+  }
+}
+
+static int mask_grid(long long BT) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long want = (BT + MS_WARPS - 1) / MS_WARPS, cap = (long long)sms * 4;
+  return (int)(want < cap ? want : cap);
 }
 
 int k_mask_stats(const float2 *spec, long long BT, int N, const float *H2, int nb, float *stats, cudaStream_t st) {
   if (BT <= 0) return 0;
-  size_t smem = sizeof(float4) * (N / 2 + 1);
-  mask_stats_kernel<<<(unsigned)BT, 256, smem, st>>>(spec, N, H2, nb, stats);
+  size_t smem = sizeof(float4) * MS_WARPS * (N / 2 + 1) + sizeof(int) * 2 * nb;
+  cudaFuncSetAttribute(mask_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  mask_stats_kernel<<<mask_grid(BT), 32 * MS_WARPS, smem, st>>>(spec, BT, N, H2, nb, stats);
   MCAG_CHECK_LAUNCH();
   return 0;
 }
@@ -140,7 +176,8 @@ int k_mask_scan(const float *stats, int B, int T, int N, int nb, int method, int
 }
 int k_mask_apply(float2 *spec, long long BT, int N, const float *H, int nb, const float *gains, cudaStream_t st) {
   if (BT <= 0) return 0;
-  mask_apply_kernel<<<(unsigned)BT, 256, sizeof(float) * nb * 2, st>>>(spec, N, H, nb, gains);
+  size_t smem = sizeof(float) * MS_WARPS * nb * 2 + sizeof(int) * 2 * (N / 2 + 1);
+  mask_apply_kernel<<<mask_grid(BT), 32 * MS_WARPS, smem, st>>>(spec, BT, N, H, nb, gains);
   MCAG_CHECK_LAUNCH();
   return 0;
 }

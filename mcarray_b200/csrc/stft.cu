@@ -122,9 +122,10 @@ __global__ void frame_power_kernel(const float2 *__restrict__ spec, long long ro
 // K7: one CTA = F consecutive hop-segments of one (stream, channel) row.  It inverse-transforms the
 // F + R - 1 frames that overlap them (R = N/hop), applies the synthesis window and sums the overlaps in frame
 // order (oldest first, as the reference's overlap-add does).  Segment indices >= T belong to the carried tail.
+// F is picked by the launcher so that F + R - 1 is a multiple of the G transform groups (every round of transforms is full).
 // ---------------------------------------------------------------------------------------------------
-template <int N, int F, int G>
-__global__ void __launch_bounds__(G *(N / 16)) istft_kernel(const float2 *__restrict__ spec, int C_in, int C_out, int T, int hop,
+template <int N, int G>
+__global__ void __launch_bounds__(G *(N / 16)) istft_kernel(const float2 *__restrict__ spec, int C_in, int C_out, int T, int hop, int F,
                                                              const float *__restrict__ win, const float2 *__restrict__ tw_g,
                                                              const float *__restrict__ tail_in, float *__restrict__ tail_out,
                                                              float *__restrict__ out, long long out_pitch, int out_rows) {
@@ -133,8 +134,8 @@ __global__ void __launch_bounds__(G *(N / 16)) istft_kernel(const float2 *__rest
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char *smem = fft_align_smem(smem_raw, 8 * NC);
   float2 *s_buf = reinterpret_cast<float2 *>(smem);                   // G * fft_buf_len(NC), each buffer aligned to its size
-  float *s_y = reinterpret_cast<float *>(s_buf + G * fft_buf_len(NC));   // (F + Rmax - 1) * N, Rmax = 4
-  float *s_w = s_y + (F + 3) * N;                                     // N
+  float *s_y = reinterpret_cast<float *>(s_buf + G * fft_buf_len(NC));   // (F + R - 1) * N
+  float *s_w = s_y + (F + R - 1) * N;                                 // N
   float2 *s_tw = reinterpret_cast<float2 *>(s_w + N);                 // fft_table_len(N): tw[NC] then twp
   float2 *s_twp = s_tw + NC;                                          // per-thread inter-pass twiddles
   float2 *s_in = s_tw + fft_table_len(N);                             // G * KP  (staged spectrum rows)
@@ -217,15 +218,21 @@ template <int N> static int launch_stft(const float *x, long long row_pitch, int
 template <int N> static int launch_istft(const float2 *spec, int B, int T, int C_in, int C_out, int hop, const float *win, const float2 *tw,
                                          const float *tail_in, float *tail_out, float *out, long long out_pitch, int out_rows, cudaStream_t st) {
   constexpr int NC = N / 2, TPF = NC / 8;
-  constexpr int F = 8;
   constexpr int G = (TPF >= 128) ? 2 : (256 / TPF);
-  size_t smem = sizeof(float) * (F + 3) * N + sizeof(float) * N + sizeof(float2) * fft_table_len(N) + sizeof(float2) * G * fft_buf_len(NC) +
-                sizeof(float2) * G * spec_pitch(N) + 8 * NC /* buffer alignment slack */;
-  auto kern = istft_kernel<N, F, G>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int R = N / hop;
+  // frames transformed per CTA: a multiple of G, about 16 but at most 64 KB of staged time-domain frames
+  int nfr = 65536 / (4 * N);
+  if (nfr > 16) nfr = 16;
+  nfr = nfr / G * G;
+  if (nfr < G) nfr = G;
+  while (nfr - (R - 1) < 1) nfr += G;
+  const int F = nfr - (R - 1);
+  size_t smem = sizeof(float) * (size_t)nfr * N + sizeof(float) * N + sizeof(float2) * fft_table_len(N) + sizeof(float2) * G * fft_buf_len(NC) +
+                sizeof(float2) * G * spec_pitch(N) + 8 * NC /* buffer alignment slack */;
+  auto kern = istft_kernel<N, G>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((T + R - 1 + F - 1) / F, B * C_out);
-  kern<<<grid, G * TPF, smem, st>>>(spec, C_in, C_out, T, hop, win, tw, tail_in, tail_out, out, out_pitch, out_rows);
+  kern<<<grid, G * TPF, smem, st>>>(spec, C_in, C_out, T, hop, F, win, tw, tail_in, tail_out, out, out_pitch, out_rows);
   MCAG_CHECK_LAUNCH();
   return 0;
 }
