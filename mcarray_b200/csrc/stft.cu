@@ -8,97 +8,119 @@
 namespace mcag {
 
 // ---------------------------------------------------------------------------------------------------
-// K1: one CTA = F consecutive frames of one (stream, channel) row.  The (F-1)*hop + N samples the frames
-// share are staged once into shared memory by a 1-D bulk async copy (TMA engine), each frame is windowed
-// while it is packed into the N/2-point complex FFT, and the one-sided spectrum is written with its Parseval
-// power.  HBM traffic per frame: hop*4 B in (+ overlap from L2), (N/2+2)*8 B out.
+// K1: persistent CTAs walk work items = F consecutive frames of one (stream, channel) row.  The window and the FFT
+// tables are loaded once per CTA; the (F-1)*hop + N samples the frames of an item share are staged into shared memory
+// by a 1-D bulk async copy (TMA engine), double-buffered so the copy of the next item runs under the transforms of the
+// current one.  Each frame is windowed while it is packed into the N/2-point complex FFT, and the one-sided spectrum is
+// written with its Parseval power.  HBM traffic per frame: hop*4 B in (+ overlap from L2), (N/2+2)*8 B out.
 // ---------------------------------------------------------------------------------------------------
 template <int N, int F, int G>
 __global__ void __launch_bounds__(G *(N / 16)) stft_kernel(const float *__restrict__ x, long long row_pitch, int M, int T, int hop,
                                                             const float *__restrict__ win, const float2 *__restrict__ tw_g,
-                                                            float2 *__restrict__ spec, float *__restrict__ chan_pow) {
-  constexpr int NC = N / 2, TPF = NC / 8, KP = spec_pitch(N), NT = G * TPF;
+                                                            float2 *__restrict__ spec, float *__restrict__ chan_pow, int tiles_per_row,
+                                                            long long n_items) {
+  constexpr int NC = N / 2, TPF = NC / 8, KP = spec_pitch(N), NT = G * TPF, XLEN = (F - 1) * N + N;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char *smem = fft_align_smem(smem_raw, 8 * NC);
   float2 *s_buf = reinterpret_cast<float2 *>(smem);                   // G * fft_buf_len(NC), each buffer aligned to its size
-  float *s_x = reinterpret_cast<float *>(s_buf + G * fft_buf_len(NC));   // (F-1)*hop_max + N floats, hop <= N
-  float *s_w = s_x + ((F - 1) * N + N);                               // N
+  float *s_xb = reinterpret_cast<float *>(s_buf + G * fft_buf_len(NC));  // 2 x ((F-1)*hop_max + N) floats, hop <= N
+  float *s_w = s_xb + 2 * XLEN;                                       // N
   float2 *s_tw = reinterpret_cast<float2 *>(s_w + N);                 // fft_table_len(N): tw[NC] then twp
   float2 *s_twp = s_tw + NC;                                          // per-thread inter-pass twiddles
   float *s_red = reinterpret_cast<float *>(s_tw + fft_table_len(N));  // G * (TPF/32 or 1)
-  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ __align__(8) uint64_t s_bar[2];
 
-  const int tid = threadIdx.x, row = blockIdx.y, t0 = blockIdx.x * F;
-  const int nf = min(F, T - t0);
-  const int nsamp = (nf - 1) * hop + N;
-  const float *src = x + (long long)row * row_pitch + (long long)t0 * hop;
-
-  const bool bulk = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((nsamp & 3) == 0);
-  if (bulk) {
-    if (tid == 0) { mbar_init(&s_bar, 1); }
-    __syncthreads();
-    if (tid == 0) {
-      mbar_expect_tx(&s_bar, (uint32_t)nsamp * 4u);
-      bulk_g2s(s_x, src, (uint32_t)nsamp * 4u, &s_bar);
-    }
-  } else {
-    for (int i = tid; i < nsamp; i += NT) s_x[i] = src[i];
-  }
+  const int tid = threadIdx.x;
+  // every item starts at a 16-byte aligned sample and has a multiple of 4 samples when this holds
+  const bool bulk = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((row_pitch & 3) == 0) && ((hop & 3) == 0);
+  if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
   for (int i = tid; i < N; i += NT) s_w[i] = win[i];
   fft_load_tables<N>(s_tw, tw_g, tid, NT);
-  if (bulk) mbar_wait(&s_bar, 0);
   __syncthreads();
+
+  auto item_src = [&](long long item, int &row, int &t0, int &nf) {
+    row = (int)(item / tiles_per_row);
+    t0 = (int)(item - (long long)row * tiles_per_row) * F;
+    nf = min(F, T - t0);
+    return x + (long long)row * row_pitch + (long long)t0 * hop;
+  };
+  auto issue = [&](long long item, int slot) {   // thread 0 only
+    int row, t0, nf;
+    const float *src = item_src(item, row, t0, nf);
+    const uint32_t bytes = (uint32_t)((nf - 1) * hop + N) * 4u;
+    mbar_expect_tx(&s_bar[slot], bytes);
+    bulk_g2s(s_xb + slot * XLEN, src, bytes, &s_bar[slot]);
+  };
 
   const int g = tid / TPF, j = tid % TPF;
   const fft_buf_t buf = smem_u32(s_buf + g * fft_buf_len(NC));
-  const int b = row / M, m = row % M;
+  if (bulk && tid == 0 && (long long)blockIdx.x < n_items) issue(blockIdx.x, 0);
+  int it = 0;
+  for (long long item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    const int slot = it & 1;
+    int row, t0, nf;
+    const float *src = item_src(item, row, t0, nf);
+    float *s_x = s_xb + slot * XLEN;
+    if (bulk) {
+      // the other slot was last read before the __syncthreads that ended the previous iteration
+      if (tid == 0 && item + gridDim.x < n_items) issue(item + gridDim.x, slot ^ 1);
+      mbar_wait(&s_bar[slot], (uint32_t)(it >> 1) & 1u);
+    } else {
+      const int nsamp = (nf - 1) * hop + N;
+      for (int i = tid; i < nsamp; i += NT) s_x[i] = src[i];
+      __syncthreads();
+    }
+    const int b = row / M, m = row - b * M;
 
-  for (int f = g; f < F; f += G) {   // uniform trip count per group; inactive frames are skipped as a group
-    if (f < nf) {
-      const float2 *xs = reinterpret_cast<const float2 *>(s_x + f * hop);   // hop is even -> 8-byte aligned
-      const float2 *ws = reinterpret_cast<const float2 *>(s_w);
-      float2 v[8];
+    for (int f = g; f < F; f += G) {   // uniform trip count per group; inactive frames are skipped as a group
+      if (f < nf) {
+        const float2 *xs = reinterpret_cast<const float2 *>(s_x + f * hop);   // hop is even -> 8-byte aligned
+        const float2 *ws = reinterpret_cast<const float2 *>(s_w);
+        float2 v[8];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int n = j + r * (NC / 8);
-        float2 a = xs[n], w = ws[n];
-        v[r] = make_float2(a.x * w.x, a.y * w.y);
-      }
-      fft_run<NC, false>(v, buf, s_twp, j, g);
-      // real post-processing: X[k] = E + W^k O, X[NC-k] = conj(E - W^k O)
-      float2 *out = spec + (((long long)b * T + (t0 + f)) * M + m) * KP;
-      float pw = 0.f;
-      for (int k = j; k <= NC / 2; k += TPF) {
-        float2 zk = fft_buf_get(buf, k), zn = fft_buf_get(buf, (NC - k) & (NC - 1));
-        float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-        float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));   // -i/2 (zk - conj zn)
-        float2 w = tw_lookup<false>(s_tw, k, NC);
-        float2 wo = cmul(w, o);
-        float2 xk = cadd(e, wo), xn = cconj(csub(e, wo));
-        if (k == 0) { xk.y = 0.f; xn.y = 0.f; }
-        out[k] = xk;
-        out[NC - k] = xn;
-        const float wk = (k == 0) ? 1.f : 2.f;
-        pw += wk * (xk.x * xk.x + xk.y * xk.y);
-        if (k != NC - k) pw += wk * (xn.x * xn.x + xn.y * xn.y);
-      }
-      if (j == 0) out[NC + 1] = make_float2(0.f, 0.f);   // pad bin
-      // Parseval power of the windowed frame, reduced in a fixed order
-      constexpr int WPF = (TPF + 31) / 32;
-      if constexpr (TPF >= 32) {   // N = 256 packs two transforms per warp: its power comes from frame_power_kernel
-        pw = warp_sum(pw);
-        if (chan_pow) {
-          if ((tid & 31) == 0) s_red[g * WPF + (j >> 5)] = pw;
-          group_sync<TPF>(g);
-          if (j == 0) {
-            float s = 0.f;
-            for (int i = 0; i < WPF; ++i) s += s_red[g * WPF + i];
-            chan_pow[((long long)b * T + (t0 + f)) * M + m] = s / ((float)N * (float)N);
+        for (int r = 0; r < 8; ++r) {
+          const int n = j + r * (NC / 8);
+          float2 a = xs[n], w = ws[n];
+          v[r] = make_float2(a.x * w.x, a.y * w.y);
+        }
+        fft_run<NC, false>(v, buf, s_twp, j, g);
+        // real post-processing: X[k] = E + W^k O, X[NC-k] = conj(E - W^k O); k = j + i*TPF (i < 4), and k = NC/2 for j = 0
+        float2 *out = spec + (((long long)b * T + (t0 + f)) * M + m) * KP;
+        float pw = 0.f;
+        auto post = [&](int k) {
+          float2 zk = fft_buf_get(buf, k), zn = fft_buf_get(buf, (NC - k) & (NC - 1));
+          float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+          float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));   // -i/2 (zk - conj zn)
+          float2 wo = cmul(s_tw[k], o);                                          // k <= NC/2 < N/2: straight from the table
+          float2 xk = cadd(e, wo), xn = cconj(csub(e, wo));
+          if (k == 0) { xk.y = 0.f; xn.y = 0.f; }
+          out[k] = xk;
+          out[NC - k] = xn;
+          const float wk = (k == 0) ? 1.f : 2.f;
+          pw += wk * (xk.x * xk.x + xk.y * xk.y);
+          if (k != NC - k) pw += wk * (xn.x * xn.x + xn.y * xn.y);
+        };
+#pragma unroll
+        for (int i = 0; i < 4; ++i) post(j + i * TPF);
+        if (j == 0) { post(NC / 2); out[NC + 1] = make_float2(0.f, 0.f); }   // middle bin and the pad bin
+        // Parseval power of the windowed frame, reduced in a fixed order
+        constexpr int WPF = (TPF + 31) / 32;
+        if constexpr (TPF >= 32) {   // N = 256 packs two transforms per warp: its power comes from frame_power_kernel
+          pw = warp_sum(pw);
+          if (chan_pow) {
+            if ((tid & 31) == 0) s_red[g * WPF + (j >> 5)] = pw;
+            group_sync<TPF>(g);
+            if (j == 0) {
+              float sacc = 0.f;
+              for (int i = 0; i < WPF; ++i) sacc += s_red[g * WPF + i];
+              chan_pow[((long long)b * T + (t0 + f)) * M + m] = sacc / ((float)N * (float)N);
+            }
           }
         }
+        group_sync<TPF>(g);
       }
-      group_sync<TPF>(g);
     }
+    __syncthreads();   // all frames of the item are done with s_x[slot] before a later copy lands in it
   }
 }
 
@@ -154,10 +176,11 @@ __global__ void __launch_bounds__(G *(N / 16)) istft_kernel(const float2 *__rest
     const int t = seg0 - (R - 1) + fi;
     float *y = s_y + fi * N;
     if (t < 0 || t >= T) {
-      for (int i = j; i < N; i += TPF) y[i] = 0.f;
+      for (int i = j; i < N / 4; i += TPF) reinterpret_cast<float4 *>(y)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
       const float2 *src = spec + (((long long)b * T + t) * C_in + c) * KP;
-      for (int k = j; k < KP; k += TPF) xin[k] = src[k];
+      for (int k = j; k < KP / 2; k += TPF)   // KP is even and rows are 16-byte aligned: two bins per load
+        reinterpret_cast<float4 *>(xin)[k] = reinterpret_cast<const float4 *>(src)[k];
       group_sync<TPF>(g);
       float2 v[8];
 #pragma unroll
@@ -172,25 +195,37 @@ __global__ void __launch_bounds__(G *(N / 16)) istft_kernel(const float2 *__rest
       }
       fft_run<NC, true>(v, buf, s_twp, j, g);
       const float sc = 1.0f / (float)NC;
-      for (int n = j; n < NC; n += TPF) {
-        float2 z = fft_buf_get(buf, n);
-        y[2 * n] = z.x * sc * s_w[2 * n];
-        y[2 * n + 1] = z.y * sc * s_w[2 * n + 1];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int n = j + r * TPF;
+        const float2 z = fft_buf_get(buf, n), w = reinterpret_cast<const float2 *>(s_w)[n];
+        reinterpret_cast<float2 *>(y)[n] = make_float2(z.x * sc * w.x, z.y * sc * w.y);
       }
       group_sync<TPF>(g);
     }
   }
   __syncthreads();
-  // overlap-add, oldest frame first; the carried tail (older still) goes in first of all
-  const int ov = N - hop;
-  for (int i = tid; i < F * hop; i += NT) {
-    const int sl = i / hop, n = i - sl * hop, seg = seg0 + sl;
-    if (seg >= T + R - 1) continue;
-    const long long pos = (long long)seg * hop + n;
-    float acc = (tail_in && pos < ov) ? tail_in[(long long)row * ov + pos] : 0.f;
-    for (int r = R - 1; r >= 0; --r) acc += s_y[(sl + (R - 1) - r) * N + n + r * hop];
-    if (seg < T) out[((long long)b * out_rows + c) * out_pitch + pos] = acc;   // out_rows >= C_out rows per stream in the caller's buffer
-    else if (tail_out) tail_out[(long long)row * ov + (pos - (long long)T * hop)] = acc;
+  // overlap-add, oldest frame first; the carried tail (older still) goes in first of all.  Four samples per thread; hop is a
+  // power of two (N / hop is 1, 2 or 4), so segment and offset are a shift and a mask.
+  const int ov = N - hop, lh = 31 - __clz(hop), q = hop >> 2;
+  float *orow = out + ((long long)b * out_rows + c) * out_pitch;
+  const bool vec = ((out_pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  for (int i4 = tid; i4 < F * q; i4 += NT) {
+    const int sl = i4 >> (lh - 2), n = (i4 & (q - 1)) << 2, seg = seg0 + sl;
+    if (seg >= T + R - 1) break;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tail_in && seg < R - 1) acc = *reinterpret_cast<const float4 *>(tail_in + (long long)row * ov + seg * hop + n);
+    for (int r = R - 1; r >= 0; --r) {
+      const float4 y4 = *reinterpret_cast<const float4 *>(s_y + (sl + (R - 1) - r) * N + n + r * hop);
+      acc.x += y4.x; acc.y += y4.y; acc.z += y4.z; acc.w += y4.w;
+    }
+    if (seg < T) {
+      float *dst = orow + (long long)seg * hop + n;
+      if (vec) *reinterpret_cast<float4 *>(dst) = acc;
+      else { dst[0] = acc.x; dst[1] = acc.y; dst[2] = acc.z; dst[3] = acc.w; }
+    } else if (tail_out) {
+      *reinterpret_cast<float4 *>(tail_out + (long long)row * ov + (seg - T) * hop + n) = acc;
+    }
   }
 }
 
@@ -198,14 +233,22 @@ template <int N> static int launch_stft(const float *x, long long row_pitch, int
                                         const float2 *tw, float2 *spec, float *chan_pow, cudaStream_t st) {
   constexpr int NC = N / 2, TPF = NC / 8;
   constexpr int G = (TPF >= 128) ? 2 : (256 / TPF);
-  constexpr int F = G > 8 ? G : 8;
-  size_t smem = sizeof(float) * ((F - 1) * N + N) + sizeof(float) * N + sizeof(float2) * fft_table_len(N) + sizeof(float2) * G * fft_buf_len(NC) +
+  constexpr int F = (N >= 2048) ? 4 : (G > 8 ? G : 8);
+  size_t smem = sizeof(float) * 2 * ((F - 1) * N + N) + sizeof(float) * N + sizeof(float2) * fft_table_len(N) + sizeof(float2) * G * fft_buf_len(NC) +
                 sizeof(float) * G * 4 + 8 * NC /* buffer alignment slack */;
   auto kern = stft_kernel<N, F, G>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  dim3 grid((T + F - 1) / F, rows);
+  static int sm_count = 0, dev_cached = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != dev_cached) { cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); dev_cached = dev; }
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, G * TPF, smem);
+  if (per_sm < 1) per_sm = 1;
+  const int tiles_per_row = (T + F - 1) / F;
+  const long long n_items = (long long)tiles_per_row * rows, cap = (long long)sm_count * per_sm;
   float *pow_in_kernel = (TPF >= 32) ? chan_pow : nullptr;
-  kern<<<grid, G * TPF, smem, st>>>(x, row_pitch, M, T, hop, win, tw, spec, pow_in_kernel);
+  kern<<<(unsigned)(n_items < cap ? n_items : cap), G * TPF, smem, st>>>(x, row_pitch, M, T, hop, win, tw, spec, pow_in_kernel, tiles_per_row, n_items);
   MCAG_CHECK_LAUNCH();
   if (chan_pow && TPF < 32) {
     long long nrows = (long long)(rows / M) * T * M;
