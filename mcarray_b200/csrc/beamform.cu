@@ -56,11 +56,14 @@ int k_ds_select(const float2 *spec, int B, int T, int M, int N, const float2 *st
   return 0;
 }
 
-// fan: CTA = (16-frame tile, 32-bin chunk, stream); the spectra tile is staged in shared memory, each thread owns one
-// (direction, bin) at a time and regenerates the M phasors once per 16 frames.
-constexpr int FAN_TF = 16, FAN_KC = 32;
-__global__ void __launch_bounds__(256) ds_fan_kernel(const float2 *__restrict__ spec, int T, int M, int N, const uint64_t *__restrict__ fx,
-                                                      int D, float2 *__restrict__ out) {
+// fan: CTA = (8-frame tile, 32-bin chunk, stream).  The spectra tile [8 frames][M][32 bins] is staged in shared memory; a
+// warp owns 4 directions at a time and each lane one bin, i.e. a register tile of 4 directions x 8 frames per thread (32 complex
+// accumulators): per microphone the 4 steering phasors are generated once (32-bit fixed-point phase, exact wrap, MUFU sin / cos)
+// and reused for the 8 frames, the 8 spectrum values are read once and reused for the 4 directions.  Channels are added in
+// index order like Beamformer.cpp:56-68.  Output rows are written 256 bytes at a time (32 consecutive bins).
+constexpr int FAN_TF = 8, FAN_TD = 4, FAN_KC = 32;
+__global__ void __launch_bounds__(256, 2) ds_fan_kernel(const float2 *__restrict__ spec, int T, int M, int N, const uint64_t *__restrict__ fx,
+                                                         int D, float2 *__restrict__ out) {
   extern __shared__ float2 s_X[];   // [FAN_TF][M][FAN_KC]
   const int KP = spec_pitch(N), K = N / 2 + 1;
   const int t0 = blockIdx.x * FAN_TF, k0 = blockIdx.y * FAN_KC, b = blockIdx.z;
@@ -70,21 +73,41 @@ __global__ void __launch_bounds__(256) ds_fan_kernel(const float2 *__restrict__ 
     s_X[i] = (t < T && k < K) ? spec[(((long long)b * T + t) * M + c) * KP + k] : make_float2(0.f, 0.f);
   }
   __syncthreads();
-  const int kk = threadIdx.x % FAN_KC, k = k0 + kk;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int k = k0 + lane;
+  if (k >= KP) return;   // no block-level synchronisation below
   const float invM = 1.0f / (float)M;
-  for (int d = threadIdx.x / FAN_KC; d < D; d += blockDim.x / FAN_KC) {
-    float2 acc[FAN_TF];
+  for (int d0 = warp * FAN_TD; d0 < D; d0 += nwarp * FAN_TD) {
+    float2 acc[FAN_TD][FAN_TF];
 #pragma unroll
-    for (int f = 0; f < FAN_TF; ++f) acc[f] = make_float2(0.f, 0.f);
+    for (int i = 0; i < FAN_TD; ++i)
+#pragma unroll
+      for (int f = 0; f < FAN_TF; ++f) acc[i][f] = make_float2(0.f, 0.f);
     for (int c = 0; c < M; ++c) {
-      const float2 a = phase_ramp(fx[(size_t)d * M + c], k);
+      float2 a[FAN_TD];
 #pragma unroll
-      for (int f = 0; f < FAN_TF; ++f) acc[f] = cadd(acc[f], cmul(s_X[(f * M + c) * FAN_KC + kk], a));
+      for (int i = 0; i < FAN_TD; ++i) {
+        const uint64_t f64 = __ldg(fx + (size_t)min(d0 + i, D - 1) * M + c);
+        const int32_t ph = (int32_t)((uint32_t)((f64 + 0x80000000ull) >> 32) * (uint32_t)k);   // signed turns * 2^32, wraps exactly
+        __sincosf((float)ph * 1.4629180792671596e-09f, &a[i].y, &a[i].x);                      // 2 pi / 2^32
+      }
+#pragma unroll
+      for (int f = 0; f < FAN_TF; ++f) {
+        const float2 xv = s_X[(f * M + c) * FAN_KC + lane];
+#pragma unroll
+        for (int i = 0; i < FAN_TD; ++i) {
+          acc[i][f].x = fmaf(xv.x, a[i].x, fmaf(-xv.y, a[i].y, acc[i][f].x));
+          acc[i][f].y = fmaf(xv.x, a[i].y, fmaf(xv.y, a[i].x, acc[i][f].y));
+        }
+      }
     }
-    if (k < KP) {
+#pragma unroll
+    for (int i = 0; i < FAN_TD; ++i) {
+      if (d0 + i >= D) break;
 #pragma unroll
       for (int f = 0; f < FAN_TF; ++f)
-        if (t0 + f < T) out[(((long long)b * T + t0 + f) * D + d) * KP + k] = (k < K) ? make_float2(acc[f].x * invM, acc[f].y * invM) : make_float2(0.f, 0.f);
+        if (t0 + f < T)
+          out[(((long long)b * T + t0 + f) * D + d0 + i) * KP + k] = (k < K) ? make_float2(acc[i][f].x * invM, acc[i][f].y * invM) : make_float2(0.f, 0.f);
     }
   }
 }
