@@ -293,6 +293,22 @@ class Cfg1Loc(Workload):
         return _threaded(lambda x: orc.freqgcc_run(self.fs, self.d, x)["idx"], list(x64), n_threads)
 
 
+class Cfg1Multiband(Cfg1Loc):
+    """MultibandBinarualLocalisation (15 linear sub-bands, 37-cell GCC-PHAT curves with 0.4 memory, energy histogram)."""
+    name = "cfg1b: 2-channel MultibandBinarualLocalisation (15 linear bands, 37 delays, 5 degree grid), 0.086 m, 16 kHz, N=512, hop=256"
+
+    def make(self, mb, B, T):
+        return mb.MultibandBinarualLocalisation(self.fs, self.d, nbins=15, usePowerFloor=False, n_streams=B, max_frames_per_call=T, frame_size=self.N,
+                                                noise_preestimated=True)
+
+    def kernel_bytes_per_frame(self):
+        K, hop, D, nb = self.N // 2 + 1, self.hop, 37, 15
+        return {"stft": 4 * 2 * hop + 8 * 2 * K, "gcc_tau": 8 * 2 * K + 4 * nb * D + 4 * nb, "curve_scan": 2 * 4 * nb * D, "select_doa": 4 * nb * D + 4 * D + 4 * nb + 8}
+
+    def cpu_run(self, orc, x64, n_threads):
+        return _threaded(lambda x: orc.multiband_run(self.fs, self.d, x)["cell"], list(x64), n_threads)
+
+
 class Cfg3(Workload):
     """32-mic linear array delay-and-sum beamformer steered to 181 azimuths, 2048-sample frames (BASELINE.json configs[2])."""
     name = "cfg3: 32-mic linear array 0.04 m pitch, delay-and-sum to 181 azimuths (spectra out), 48 kHz, N=2048, hop=1024"
@@ -333,7 +349,7 @@ class Cfg3(Workload):
         return _threaded(lambda x: orc.ds_fan(orc.stft(x, self.N, self.hop), self.N, self.fs, xs, self.doas()).shape, list(x64), n_threads)
 
 
-WORKLOADS = {"cfg1m": Cfg1Mask, "cfg1l": Cfg1Loc, "cfg2": Cfg2, "cfg3": Cfg3, "cfg4": Cfg4, "cfg4s": Cfg4Sharded, "cfg5": Cfg5}
+WORKLOADS = {"cfg1m": Cfg1Mask, "cfg1l": Cfg1Loc, "cfg1b": Cfg1Multiband, "cfg2": Cfg2, "cfg3": Cfg3, "cfg4": Cfg4, "cfg4s": Cfg4Sharded, "cfg5": Cfg5}
 
 
 # ----------------------------------------------------------------------------------------------------------------------

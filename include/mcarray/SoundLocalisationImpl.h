@@ -17,7 +17,7 @@ class LocalisingProcessor : public ShortTimeProcessor {
   void setCallback(LocalisationCallback *callback) { _callback = callback; }
 
   /** grid cell -> DOA in radians (doaIdx2angle, microhponeArrayHelpers.cpp:117-120); cell n_dirs is the initial DOA of 0 */
-  double cellAngle(int cell) const { return cell >= _info.n_dirs ? 0.0 : mcag_geom_cell_angle(cell, _doaStep); }
+  double cellAngle(int cell) const { return (cell < 0 || cell >= _info.n_dirs) ? 0.0 : mcag_geom_cell_angle(cell, _doaStep); }
 
  protected:
   LocalisingProcessor() : _callback(NULL), _doaStep(0), _cellsPerFrame(1) {}

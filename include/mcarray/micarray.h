@@ -6,6 +6,7 @@
 #include <mcarray/BeamformingSeparationAndLocalistaion.h>
 #include <mcarray/BinauralLocalisation.h>
 #include <mcarray/FastBinauralMasking.h>
+#include <mcarray/MultibandBinarualLocalisation.h>
 #include <mcarray/SourceLocalisation.h>
 #include <mcarray/SourceSeparationAndLocalisation.h>
 #endif

@@ -50,7 +50,8 @@ enum {
   MCAG_KIND_MASK = 3,     /* FastBinauralMasking: STFT -> 45-band spatial/temporal mask -> OLA */
   MCAG_KIND_TDOA = 4,     /* integer-lag GCC-PHAT on all pairs (BASELINE config 2) */
   MCAG_KIND_DSFAN = 5,    /* delay-and-sum to a fan of D azimuths, spectra out (BASELINE config 3) */
-  MCAG_KIND_SRP = 6       /* SRP-PHAT map over a large grid, channel form (BASELINE config 4) */
+  MCAG_KIND_SRP = 6,      /* SRP-PHAT map over a large grid, channel form (BASELINE config 4) */
+  MCAG_KIND_MULTIBAND = 7 /* MultibandBinarualLocalisation: per sub-band GCC-PHAT curves (0.4 memory) + energy-weighted DOA histogram */
 };
 
 /* result arrays (mcag_fetch_* / mcag_device_ptr); shapes use T = frames of the last process call */
@@ -66,7 +67,9 @@ enum {
   MCAG_OUT_ACTIVE = 8,    /* uint8  [B][T]            1 where the power gate let the frame through */
   MCAG_OUT_BEAMS = 9,     /* float2 [B][T][C][N/2+2]  beamformed / masked spectra (SSL, MASK, DSFAN: C = D) */
   MCAG_OUT_MASK_Q = 10,   /* float  [B][T][nb]        short-time band power after each frame (MASK) */
-  MCAG_OUT_MASK_DEC = 11  /* uint8  [B][T][nb]        2 = spatial mask, 1 = temporal mask, 0 = pass (MASK) */
+  MCAG_OUT_MASK_DEC = 11, /* uint8  [B][T][nb]        2 = spatial mask, 1 = temporal mask, 0 = pass (MASK) */
+  MCAG_OUT_BAND_CELL = 12 /* int32  [B][T][nb]        arg-max cell of each sub-band curve (MULTIBAND); its MCAG_OUT_CURVES is [B][T][nb][D],
+                             MCAG_OUT_ENERGY the energy-weighted histogram [B][T][D], MCAG_OUT_CELL / _PROB [B][T] */
 };
 
 enum {                    /* emit flags: keep optional intermediates of the last call fetchable */
@@ -213,6 +216,9 @@ void mcag_geom_mic_tau(const double *mic_xyz, int M, int fs, const double *dirs 
 void mcag_geom_pair_tau_from_mic_tau(const double *mic_tau, int M, int D, double *pair_tau /* [P][D] */);
 void mcag_geom_mel_bank(int N, int n_bands, int fs, float lo, float hi, double mic_dist, double *H /* [nb][N/2+1] */,
                         double *fc_norm /* [nb] */, double *thresholds /* [nb] */);
+/* MultibandBinarualLocalisation constructor (MultibandBinarualLocalisation.cpp:52-101): D = floor(pi/step)+1 delays tau [D] on the
+ * 5 degree grid, n_bands linear bands between 100 Hz and c/(2 d) (maxFreqForSpatialAliasing).  Returns D; tau / H may be NULL. */
+int mcag_geom_multiband(int fs, double mic_dist, int N, int n_bands, double *tau /* [D] */, double *H /* [nb][N/2+1] */);
 
 #ifdef __cplusplus
 }

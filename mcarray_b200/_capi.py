@@ -8,9 +8,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmcarray_b200.so")
 
-KIND_SSL, KIND_SL, KIND_FREQGCC, KIND_MASK, KIND_TDOA, KIND_DSFAN, KIND_SRP = range(7)
+KIND_SSL, KIND_SL, KIND_FREQGCC, KIND_MASK, KIND_TDOA, KIND_DSFAN, KIND_SRP, KIND_MULTIBAND = range(8)
 (OUT_SPECTRA, OUT_POWER_DB, OUT_CORR, OUT_ENERGY, OUT_CELL, OUT_PROB, OUT_LAGS, OUT_CURVES, OUT_ACTIVE, OUT_BEAMS,
- OUT_MASK_Q, OUT_MASK_DEC) = range(12)
+ OUT_MASK_Q, OUT_MASK_DEC, OUT_BAND_CELL) = range(13)
 EMIT_CORR, EMIT_CURVES, EMIT_SPECTRA = 1, 2, 4
 
 c_dp = C.POINTER(C.c_double)
@@ -127,6 +127,13 @@ def pair_tau_from_mic_tau(mt):
     t = np.zeros((M * (M - 1) // 2, D))
     lib().mcag_geom_pair_tau_from_mic_tau(dp(mt), M, D, dp(t))
     return t
+
+
+def multiband_setup(fs, mic_dist, N, nb):
+    D = lib().mcag_geom_multiband(int(fs), C.c_double(mic_dist), int(N), int(nb), None, None)
+    tau = np.zeros(D); H = np.zeros((nb, N // 2 + 1))
+    lib().mcag_geom_multiband(int(fs), C.c_double(mic_dist), int(N), int(nb), dp(tau), dp(H))
+    return tau, H
 
 
 def mel_bank(N, nb, fs, lo, hi, mic_dist):

@@ -184,6 +184,7 @@ struct mcag_proc_s {
   DevBuf lags, curves, curve_state, started;
   DevBuf mic_fx, srp_ws;
   DevBuf H, H2, thr, stats, gains, Q, noise, dec, qtrace;
+  DevBuf band_raw, band_energy, floor_pow, band_cells, mb_raw_cell, mb_raw_prob;
   void *pin_in = nullptr, *pin_out = nullptr; size_t pin_in_bytes = 0, pin_out_bytes = 0;
   std::vector<double> h_window;
   // per-kernel CUDA-event timing (mcag_profile_*): events are recorded on the handle's own stream around each launch
@@ -241,7 +242,11 @@ static int init_state(mcag_proc p) {
   if (p->energy_state.p) CU(cudaMemsetAsync(p->energy_state.p, 0, p->energy_state.bytes, st));
   if (p->curve_state.p) CU(cudaMemsetAsync(p->curve_state.p, 0, p->curve_state.bytes, st));
   if (p->started.p) CU(cudaMemsetAsync(p->started.p, 0, p->started.bytes, st));
-  if (p->cell_state.p) {
+  if (p->cell_state.p && p->cfg.kind == MCAG_KIND_MULTIBAND) {
+    std::vector<int32_t> c((size_t)p->B, -1);              // no cell yet: _currentDOA = 0 rad (MultibandBinarualLocalisation.cpp:78)
+    CU(cudaMemcpyAsync(p->cell_state.p, c.data(), c.size() * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+  } else if (p->cell_state.p) {
     std::vector<int32_t> c((size_t)p->B * p->S, p->D);     // row D of the steering table = the initial DOA of 0 rad (BSAL.cpp:51)
     std::vector<float> pr((size_t)p->B * p->S, -1.0f);     // wipp::set(-1.0, _prob) (BSAL.cpp:52)
     CU(cudaMemcpyAsync(p->cell_state.p, c.data(), c.size() * 4, cudaMemcpyHostToDevice, st));
@@ -278,7 +283,7 @@ int mcag_create(const mcag_config *cfg, mcag_proc *out) {
   if (cfg->hop <= 0 || (N % cfg->hop) || (cfg->hop & 3) || N / cfg->hop > 4) return mcag_set_error(MCAG_ERR_INVALID, "hop must divide N (N/hop <= 4) and be a multiple of 4");
   if (cfg->n_channels < 1 || cfg->n_streams < 1 || cfg->max_frames_per_call < 1) return mcag_set_error(MCAG_ERR_INVALID, "bad channel / stream / frame counts");
   const int kind = cfg->kind;
-  if ((kind == MCAG_KIND_MASK || kind == MCAG_KIND_FREQGCC) && cfg->n_channels != 2)
+  if ((kind == MCAG_KIND_MASK || kind == MCAG_KIND_FREQGCC || kind == MCAG_KIND_MULTIBAND) && cfg->n_channels != 2)
     return mcag_set_error(MCAG_ERR_INVALID, "Binaural masking is only working for 2 channels.");   // FastBinauralMasking.cpp:88-91
   CU(cudaSetDevice(cfg->device));
 
@@ -371,6 +376,24 @@ int mcag_create(const mcag_config *cfg, mcag_proc *out) {
         (rc = p->cells.alloc(4 * B * T)))
       return fail(rc);
   }
+  if (kind == MCAG_KIND_MULTIBAND) {
+    const size_t nb = cfg->n_bands;
+    if (D < 2 || !cfg->pair_tau || nb < 1 || !cfg->band_coefs) return fail(mcag_set_error(MCAG_ERR_INVALID, "pair_tau [D] and band_coefs [nb][N/2+1] required"));
+    std::vector<double> turns(D);
+    for (size_t i = 0; i < D; ++i) turns[i] = cfg->pair_tau[i] / (double)N;   // exp(+j 2 pi k tau / N)
+    if ((rc = upload_fx(p->pair_fx, turns.data(), D, st))) return fail(rc);
+    if ((rc = p->steer_tab.alloc(sizeof(float2) * D * KP))) return fail(rc);   // phasor table W[d][k], L2-resident (76 KB at D = 37, N = 512)
+    if ((rc = k_steer_table(p->pair_fx.as<uint64_t>(), (int)D, N, p->steer_tab.as<float2>(), st))) return fail(rc);
+    std::vector<float> H(nb * KP, 0.f);
+    for (size_t b = 0; b < nb; ++b) for (int k = 0; k < p->K; ++k) H[b * KP + k] = (float)cfg->band_coefs[b * p->K + k];
+    if ((rc = upload(p->H, H.data(), H.size() * 4, st))) return fail(rc);
+    CU(cudaStreamSynchronize(st));
+    if ((rc = p->band_raw.alloc(4 * B * T * nb * D)) || (rc = p->curves.alloc(4 * B * T * nb * D)) || (rc = p->curve_state.alloc(4 * B * nb * D)) ||
+        (rc = p->band_energy.alloc(4 * B * T * nb)) || (rc = p->floor_pow.alloc(4 * B * T)) || (rc = p->energy.alloc(4 * B * T * D)) ||
+        (rc = p->band_cells.alloc(4 * B * T * nb)) || (rc = p->mb_raw_cell.alloc(4 * B * T)) || (rc = p->mb_raw_prob.alloc(4 * B * T)) ||
+        (rc = p->cells.alloc(4 * B * T)) || (rc = p->prob.alloc(4 * B * T)) || (rc = p->cell_state.alloc(4 * B)))
+      return fail(rc);
+  }
   if (kind == MCAG_KIND_TDOA) {
     if (p->M < 2) return fail(mcag_set_error(MCAG_ERR_INVALID, "TDOA needs at least 2 channels"));
     if ((rc = p->lags.alloc(4 * B * T * P))) return fail(rc);
@@ -424,7 +447,7 @@ void mcag_destroy(mcag_proc p) {
                    &p->active, &p->gate, &p->pair_fx, &p->corr, &p->esum, &p->energy, &p->energy_state, &p->raw_idx, &p->raw_prob, &p->cells,
                    &p->prob, &p->cell_state, &p->prob_state, &p->steer_fx, &p->steer_tab, &p->beams, &p->tail[0], &p->tail[1], &p->out_dev,
                    &p->lags, &p->curves, &p->curve_state, &p->started, &p->mic_fx, &p->srp_ws, &p->H, &p->H2, &p->thr, &p->stats, &p->gains, &p->Q,
-                   &p->noise, &p->dec, &p->qtrace};
+                   &p->noise, &p->dec, &p->qtrace, &p->band_raw, &p->band_energy, &p->floor_pow, &p->band_cells, &p->mb_raw_cell, &p->mb_raw_prob};
   for (DevBuf *b : all) b->release();
   for (auto &r : p->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (cudaEvent_t e : p->prof_pool) cudaEventDestroy(e);
@@ -551,7 +574,7 @@ static int run_frames(mcag_proc p, const float *x_all, long long pitch, int T, i
     OK(k_stft(x, pitch, B * M, M, T, N, hop, win, tw, spec, chan_pow, st));
     p->launches += (N == 256) ? 2 : 1;
   }
-  {
+  if (kind != MCAG_KIND_MULTIBAND) {
     PROF(MCAG_PROF_GATE);
     if (p->cfg.floor_ccs_power) { OK(k_frame_power_raw(spec, BT * M, N, chan_raw, st)); p->launches++; }
     const int needed = (int)(p->cfg.floor_seconds * (float)p->cfg.sample_rate);
@@ -635,6 +658,31 @@ static int run_frames(mcag_proc p, const float *x_all, long long pitch, int T, i
       OK(k_curve_scan_argmax(corr, B, T, D, 1.0f, p->cfg.corr_memory, active, p->curve_state.as<float>() + o * D,
                              p->started.as<unsigned char>() + o, p->curves.as<float>() + o * T * D, p->cells.as<int32_t>() + o * T, st));
       p->launches += 3;
+    }
+  } else if (kind == MCAG_KIND_MULTIBAND) {
+    const int nb_ = p->cfg.n_bands;
+    float *band_raw = p->band_raw.as<float>() + o * T * nb_ * D, *curves = p->curves.as<float>() + o * T * nb_ * D;
+    float *band_energy = p->band_energy.as<float>() + o * T * nb_, *floor_pow = p->floor_pow.as<float>() + o * T;
+    int32_t *raw_cell = p->mb_raw_cell.as<int32_t>() + o * T;
+    float *raw_prob = p->mb_raw_prob.as<float>() + o * T;
+    {
+      PROF(MCAG_PROF_GCC_TAU);
+      OK(k_mb_band(spec, BT, N, p->H.as<float>(), nb_, p->steer_tab.as<float2>(), D, band_raw, band_energy, floor_pow, st));
+      p->launches++;
+    }
+    {
+      PROF(MCAG_PROF_CURVE_SCAN);
+      OK(k_mb_scan(band_raw, B, T, nb_, D, p->cfg.corr_memory, p->curve_state.as<float>() + o * nb_ * D, curves, st));
+      p->launches++;
+    }
+    {
+      PROF(MCAG_PROF_SELECT_DOA);
+      OK(k_mb_summary(curves, band_energy, BT, nb_, D, p->energy.as<float>() + o * T * D, p->band_cells.as<int32_t>() + o * T * nb_, raw_cell, raw_prob, st));
+      const int needed = (int)(p->cfg.floor_seconds * (float)p->cfg.sample_rate);
+      OK(k_mb_gate(floor_pow, chan_pow, raw_cell, raw_prob, B, T, N, p->cfg.use_power_floor, p->cfg.noise_margin_db, needed,
+                   p->gate.as<GateState>() + o, p->cell_state.as<int32_t>() + o, p->power_db.as<float>() + o * T, active,
+                   p->cells.as<int32_t>() + o * T, p->prob.as<float>() + o * T, st));
+      p->launches += 2;
     }
   } else if (kind == MCAG_KIND_DSFAN) {
     PROF(MCAG_PROF_DS_FAN);
@@ -915,6 +963,7 @@ static const DevBuf *result_buf(mcag_proc p, int what) {
     case MCAG_OUT_BEAMS: return p->cfg.kind == MCAG_KIND_MASK ? &p->spec : &p->beams;
     case MCAG_OUT_MASK_Q: return &p->qtrace;
     case MCAG_OUT_MASK_DEC: return &p->dec;
+    case MCAG_OUT_BAND_CELL: return &p->band_cells;
   }
   return nullptr;
 }

@@ -99,4 +99,30 @@ void mcag_geom_mel_bank(int N, int n_bands, int fs, float lo, float hi, double m
   }
 }
 
+/* MultibandBinarualLocalisation.cpp:52-101; the linear bank is the DSPONE SubBandSTFTAnalysis stand-in (oracle/CONVENTIONS.md C8):
+ * triangular unit-peak responses whose centres are equally spaced in Hz between 100 Hz and maxFreqForSpatialAliasing. */
+int mcag_geom_multiband(int fs, double mic_dist, int N, int n_bands, double *tau, double *H) {
+  const float step = float(5 * M_PI / 180);
+  const int D = int(std::floor(M_PI / step) + 1);                                      // :63
+  if (tau)
+    for (int d = 0; d < D; ++d) tau[d] = delay_samples(doa_idx_to_angle(d, step), float(mic_dist), fs);   // :99
+  if (H) {
+    const int K = N / 2 + 1;
+    const float lo_f = 100, hi_f = float(kSpeedOfSound / (2 * float(mic_dist)));        // microhponeArrayHelpers.cpp:85-89
+    std::vector<double> edges(size_t(n_bands) + 2);
+    for (int i = 0; i < n_bands + 2; ++i) edges[size_t(i)] = double(lo_f) + (double(hi_f) - double(lo_f)) * double(i) / double(n_bands + 1);
+    for (int b = 0; b < n_bands; ++b) {
+      const double l = edges[size_t(b)], mid = edges[size_t(b) + 1], h = edges[size_t(b) + 2];
+      for (int k = 0; k < K; ++k) {
+        const double f = double(k) * double(fs) / double(N);
+        double v = 0.0;
+        if (f > l && f <= mid) v = (f - l) / (mid - l);
+        else if (f > mid && f < h) v = (h - f) / (h - mid);
+        H[(long long)b * K + k] = v;
+      }
+    }
+  }
+  return D;
+}
+
 }  // extern "C"

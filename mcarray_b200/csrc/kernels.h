@@ -49,4 +49,14 @@ int k_mask_scan(const float *stats, int B, int T, int N, int nb, int method, int
                 int first_call, float *gains, unsigned char *decisions, float *q_trace, cudaStream_t st);
 int k_mask_apply(float2 *spec, long long BT, int N, const float *H, int nb, const float *gains, cudaStream_t st);
 
+// multiband.cu
+int k_mb_band(const float2 *spec, long long BT, int N, const float *H, int nb, const float2 *W, int D, float *band_raw, float *band_energy,
+              float *floor_pow, cudaStream_t st);
+int k_mb_scan(const float *raw, int B, int T, int nb, int D, float mem, float *state, float *curves, cudaStream_t st);
+int k_mb_summary(const float *curves, const float *band_energy, long long BT, int nb, int D, float *hist, int32_t *band_cells, int32_t *raw_cell,
+                 float *raw_prob, cudaStream_t st);
+int k_mb_gate(const float *floor_pow, const float *chan_pow, const int32_t *raw_cell, const float *raw_prob, int B, int T, int N, int use_floor,
+              float margin_db, int needed, void *gate_state, int32_t *cell_state, float *power_out, unsigned char *active, int32_t *cells, float *prob,
+              cudaStream_t st);
+
 }  // namespace mcag

@@ -1,0 +1,205 @@
+// N2 multiband binaural localisation: MultibandBinarualLocalisation::processOneSubband / processSumamry
+// (MultibandBinarualLocalisation.cpp:145-259).  Per linear sub-band a GCC-PHAT curve on the DOA grid with 0.4 memory and
+// its arg-max, then an energy-weighted histogram of the band arg-maxima whose own arg-max is the published DOA.
+//   band    : per frame, the raw band curves sum_{k in band} Re(G[k] W[d][k]), the band energies and the floor power
+//   scan    : c = (1-m) raw + m prev over frames, per (stream, band, delay)                                   (:180-183)
+//   summary : band arg-maxima, histogram in band order, its sum / arg-max / prob                                (:184-233)
+//   gate    : the power-floor state machine and the hold of the published cell on silent frames              (:127-143,214-255)
+// PHAT whitening makes the band response drop out of G wherever it is non-zero, so the band curves share one whitened
+// cross-spectrum per frame and differ only in the bins they add.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mcag {
+
+constexpr int MB_WARPS = 8;
+
+__global__ void __launch_bounds__(32 * MB_WARPS) mb_band_kernel(const float2 *__restrict__ spec, long long BT, int N, const float *__restrict__ H,
+                                                                int nb, const float2 *__restrict__ W, int D, float *__restrict__ band_raw,
+                                                                float *__restrict__ band_energy, float *__restrict__ floor_pow) {
+  extern __shared__ float2 s_all[];   // [MB_WARPS][K] whitened cross-spectrum, then [MB_WARPS][K] weighted bin power, then band ranges
+  const int KP = spec_pitch(N), K = N / 2 + 1;
+  float *s_pw_all = reinterpret_cast<float *>(s_all + (size_t)MB_WARPS * K);
+  int *s_lo = reinterpret_cast<int *>(s_pw_all + (size_t)MB_WARPS * K), *s_hi = s_lo + nb;
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+    const float *h = H + (size_t)b * KP;
+    int lo = K, hi = 0;
+    for (int k = 0; k < K; ++k)
+      if (h[k] != 0.f) { lo = min(lo, k); hi = k + 1; }
+    s_lo[b] = lo; s_hi[b] = hi;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2 *s_G = s_all + (size_t)warp * K;
+  float *s_pw = s_pw_all + (size_t)warp * K;
+  const int KF = K / 2;                                         // FFTPower(frames, K): the first K/2 bins of the CCS buffer (:130)
+  const float nF = (float)(K - 2);
+  for (long long bt = (long long)blockIdx.x * MB_WARPS + warp; bt < BT; bt += (long long)gridDim.x * MB_WARPS) {
+    const float2 *L = spec + bt * 2 * KP, *R = L + KP;
+    float fl = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float2 l = L[k], r = R[k];
+      s_G[k] = whiten(cmulc(l, r));
+      const float p = l.x * l.x + l.y * l.y + r.x * r.x + r.y * r.y;
+      s_pw[k] = ((k == 0 || k == K - 1) ? 1.f : 2.f) * p;
+      if (k < KF) fl += ((k == 0 || k == KF - 1) ? 1.f : 2.f) * p;
+    }
+    fl = warp_sum(fl);
+    if (lane == 0) floor_pow[bt] = 0.5f * fl / (nF * nF);       // mean over the two channels
+    __syncwarp();
+    for (int i = lane; i < nb * D; i += 32) {
+      const int b = i / D, d = i - b * D;
+      const float *h = H + (size_t)b * KP;
+      const float2 *w = W + (size_t)d * KP;
+      float acc = 0.f;
+      const int hi = s_hi[b];
+      for (int k = s_lo[b]; k < hi; ++k) {
+        if (__ldg(h + k) == 0.f) continue;
+        const float2 g = s_G[k], a = __ldg(w + k);
+        acc = fmaf(g.x, a.x, fmaf(-g.y, a.y, acc));
+      }
+      band_raw[(bt * nb + b) * D + d] = acc;
+    }
+    for (int b = lane; b < nb; b += 32) {                       // FFTPower of the band frame (:188), mean over the two channels
+      const float *h = H + (size_t)b * KP;
+      float acc = 0.f;
+      const int hi = s_hi[b];
+      for (int k = s_lo[b]; k < hi; ++k) { const float hv = __ldg(h + k); acc = fmaf(hv * hv, s_pw[k], acc); }
+      band_energy[bt * nb + b] = 0.5f * acc / ((float)N * (float)N);
+    }
+    __syncwarp();
+  }
+}
+
+// one thread per (stream, band, delay); arithmetic in the reference's order: c *= (1-m); prev *= m; c += prev; prev = c
+__global__ void mb_scan_kernel(const float *__restrict__ raw, int B, int T, int nbD, float mem, float *__restrict__ state, float *__restrict__ curves) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * nbD) return;
+  const int s = i / nbD, e = i - s * nbD;
+  const float keep = 1.0f - mem;
+  float prev = state[i];
+  for (int t = 0; t < T; ++t) {
+    const long long o = ((long long)s * T + t) * nbD + e;
+    const float c = __fadd_rn(__fmul_rn(raw[o], keep), __fmul_rn(prev, mem));
+    curves[o] = c;
+    prev = c;
+  }
+  state[i] = prev;
+}
+
+// one warp per frame
+__global__ void __launch_bounds__(32 * MB_WARPS) mb_summary_kernel(const float *__restrict__ curves, const float *__restrict__ band_energy,
+                                                                   long long BT, int nb, int D, float *__restrict__ hist_out,
+                                                                   int32_t *__restrict__ band_cells, int32_t *__restrict__ raw_cell,
+                                                                   float *__restrict__ raw_prob) {
+  extern __shared__ float s_hist_all[];   // [MB_WARPS][D]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long bt = (long long)blockIdx.x * MB_WARPS + warp;
+  if (bt >= BT) return;
+  float *hist = s_hist_all + (size_t)warp * D;
+  for (int d = lane; d < D; d += 32) hist[d] = 0.f;
+  __syncwarp();
+  for (int b = 0; b < nb; ++b) {
+    const float *c = curves + (bt * nb + b) * D;
+    float bv = -3.0e38f; int bi = 0x7fffffff;
+    for (int d = lane; d < D; d += 32) { const float v = c[d]; if (v > bv) { bv = v; bi = d; } }
+    warp_argmax(bv, bi);                                         // wipp::maxidx: first maximum (:184)
+    if (lane == 0) {
+      hist[bi] += band_energy[bt * nb + b];                      // _energyInDOA[idx] += _energies[bin], bands in order (:190)
+      band_cells[bt * nb + b] = bi;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    float sum = 0.f, mx = hist[0]; int mi = 0;
+    for (int d = 0; d < D; ++d) { const float v = hist[d]; sum += v; if (v > mx) { mx = v; mi = d; } }   // wipp::sum / maxidx (:222-223)
+    raw_cell[bt] = mi;
+    raw_prob[bt] = (sum != 0.f) ? hist[mi] / sum : sum;          // :225-228
+  }
+  __syncwarp();
+  for (int d = lane; d < D; d += 32) hist_out[bt * D + d] = hist[d];
+}
+
+struct MbGateState { double acc; double floor; int samples; int estimated; };   // same layout as the processors' GateState
+
+// one thread per stream, sequential over the frames of the call
+__global__ void mb_gate_kernel(const float *__restrict__ floor_pow, const float *__restrict__ chan_pow, const int32_t *__restrict__ raw_cell,
+                               const float *__restrict__ raw_prob, int B, int T, int N, int use_floor, float margin_db, int needed,
+                               MbGateState *__restrict__ gs, int32_t *__restrict__ cell_state, float *__restrict__ power_out,
+                               unsigned char *__restrict__ active, int32_t *__restrict__ cells, float *__restrict__ prob) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= B) return;
+  MbGateState g = gs[s];
+  int32_t cur = cell_state[s];
+  const int K = N / 2 + 1;
+  for (int t = 0; t < T; ++t) {
+    const long long bt = (long long)s * T + t;
+    double power;
+    if (!g.estimated) {                                          // setPowerFloor (:127-143)
+      g.acc += (double)floor_pow[bt] * (double)(2 * K - 2);
+      g.samples += 2 * K - 2;
+      if (g.samples >= needed) {
+        g.estimated = 1;
+        g.acc /= (double)g.samples;
+        g.acc = 10.0 * log10(g.acc) + (double)margin_db;
+      }
+      g.floor = g.acc;
+      power = g.floor;
+    } else {
+      power = 0.5 * ((double)chan_pow[bt * 2] + (double)chan_pow[bt * 2 + 1]);   // FFTPower(frames, N+2) (:221)
+    }
+    const bool on = (power > g.floor) || !use_floor;             // :225
+    if (on) cur = raw_cell[bt];
+    cells[bt] = cur;
+    prob[bt] = on ? raw_prob[bt] : -100000.f;                    // :253
+    power_out[bt] = (float)power;
+    active[bt] = on ? 1 : 0;
+  }
+  gs[s] = g;
+  cell_state[s] = cur;
+}
+
+static int mb_grid(long long BT) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long want = (BT + MB_WARPS - 1) / MB_WARPS, cap = (long long)sms * 4;
+  return (int)(want < cap ? want : cap);
+}
+
+int k_mb_band(const float2 *spec, long long BT, int N, const float *H, int nb, const float2 *W, int D, float *band_raw, float *band_energy,
+              float *floor_pow, cudaStream_t st) {
+  if (BT <= 0) return 0;
+  const int K = N / 2 + 1;
+  size_t smem = (sizeof(float2) + sizeof(float)) * MB_WARPS * K + sizeof(int) * 2 * nb;
+  cudaFuncSetAttribute(mb_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  mb_band_kernel<<<mb_grid(BT), 32 * MB_WARPS, smem, st>>>(spec, BT, N, H, nb, W, D, band_raw, band_energy, floor_pow);
+  MCAG_CHECK_LAUNCH();
+  return 0;
+}
+int k_mb_scan(const float *raw, int B, int T, int nb, int D, float mem, float *state, float *curves, cudaStream_t st) {
+  if (B <= 0 || T <= 0) return 0;
+  const int n = B * nb * D;
+  mb_scan_kernel<<<(n + 127) / 128, 128, 0, st>>>(raw, B, T, nb * D, mem, state, curves);
+  MCAG_CHECK_LAUNCH();
+  return 0;
+}
+int k_mb_summary(const float *curves, const float *band_energy, long long BT, int nb, int D, float *hist, int32_t *band_cells, int32_t *raw_cell,
+                 float *raw_prob, cudaStream_t st) {
+  if (BT <= 0) return 0;
+  mb_summary_kernel<<<(unsigned)((BT + MB_WARPS - 1) / MB_WARPS), 32 * MB_WARPS, sizeof(float) * MB_WARPS * D, st>>>(curves, band_energy, BT, nb, D, hist,
+                                                                                                                    band_cells, raw_cell, raw_prob);
+  MCAG_CHECK_LAUNCH();
+  return 0;
+}
+int k_mb_gate(const float *floor_pow, const float *chan_pow, const int32_t *raw_cell, const float *raw_prob, int B, int T, int N, int use_floor,
+              float margin_db, int needed, void *gate_state, int32_t *cell_state, float *power_out, unsigned char *active, int32_t *cells, float *prob,
+              cudaStream_t st) {
+  if (B <= 0 || T <= 0) return 0;
+  mb_gate_kernel<<<(B + 63) / 64, 64, 0, st>>>(floor_pow, chan_pow, raw_cell, raw_prob, B, T, N, use_floor, margin_db, needed,
+                                               static_cast<MbGateState *>(gate_state), cell_state, power_out, active, cells, prob);
+  MCAG_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace mcag

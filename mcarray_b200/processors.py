@@ -19,7 +19,8 @@ MaskingAlg = dict(BOTH=0, SPATIAL=1, TEMPORAL=2)                          # Arra
 
 _OUT_DTYPE = {capi.OUT_SPECTRA: np.complex64, capi.OUT_POWER_DB: np.float32, capi.OUT_CORR: np.float32, capi.OUT_ENERGY: np.float32,
               capi.OUT_CELL: np.int32, capi.OUT_PROB: np.float32, capi.OUT_LAGS: np.int32, capi.OUT_CURVES: np.float32,
-              capi.OUT_ACTIVE: np.uint8, capi.OUT_BEAMS: np.complex64, capi.OUT_MASK_Q: np.float32, capi.OUT_MASK_DEC: np.uint8}
+              capi.OUT_ACTIVE: np.uint8, capi.OUT_BEAMS: np.complex64, capi.OUT_MASK_Q: np.float32, capi.OUT_MASK_DEC: np.uint8,
+              capi.OUT_BAND_CELL: np.int32}
 
 
 _default_device = 0
@@ -213,6 +214,59 @@ class FreqGCCBinauralLocalisation(Processor):
 
     def cells(self):
         return self.fetch(capi.OUT_CELL, self._bt())
+
+
+class MultibandBinarualLocalisation(Processor):
+    """MultibandBinarualLocalisation(sampleRate, microphonePositions, nbins=15, usePowerFloor) — include/mcarray/MultibandBinarualLocalisation.h:40;
+    here the two-microphone array is given by its spacing."""
+
+    def __init__(self, sampleRate, microphoneDistance, nbins=15, usePowerFloor=True, n_streams=1, max_frames_per_call=256, frame_size=None,
+                 noise_preestimated=False):
+        self.doa_step = np.float32(5 * np.pi / 180)                         # MultibandBinarualLocalisation.cpp:62
+        N = frame_size or capi.frame_size(sampleRate, 0.025)                # _frameRate, .h:41
+        tau, H = capi.multiband_setup(sampleRate, microphoneDistance, N, nbins)
+        super().__init__(kind=capi.KIND_MULTIBAND, sample_rate=sampleRate, frame_size=N, hop=N // 2, n_channels=2, n_streams=n_streams,
+                         max_frames_per_call=max_frames_per_call, n_dirs=len(tau), pair_tau=tau, n_bands=nbins, band_coefs=H,
+                         use_power_floor=int(usePowerFloor), noise_margin_db=3.0, noise_preestimated=int(noise_preestimated),
+                         corr_memory=float(np.float32(0.4)))               # _corrMemoryFactor, .h:44
+        self.nbins, self.H, self.tau = nbins, H, tau
+        self._callback = None
+
+    def setCallback(self, cb):
+        self._callback = cb
+
+    def cells(self):
+        return self.fetch(capi.OUT_CELL, self._bt())
+
+    def prob(self):
+        return self.fetch(capi.OUT_PROB, self._bt())
+
+    def histogram(self):
+        B, T = self._bt()
+        return self.fetch(capi.OUT_ENERGY, (B, T, self.info.n_dirs))
+
+    def band_cells(self):
+        B, T = self._bt()
+        return self.fetch(capi.OUT_BAND_CELL, (B, T, self.nbins))
+
+    def band_curves(self):
+        B, T = self._bt()
+        return self.fetch(capi.OUT_CURVES, (B, T, self.nbins, self.info.n_dirs))
+
+    def doa_deg(self, cells=None):
+        cells = self.cells() if cells is None else cells
+        ang = np.array([capi.cell_angle(i, self.doa_step) for i in range(self.info.n_dirs)] + [0.0])   # cell -1: the initial DOA of 0 rad
+        return ang[cells] * (180 / np.pi)
+
+    def process(self, x):
+        y = super().process(x)
+        if self._callback is not None and self.frames_done:
+            doa, prob, power, act = self.doa_deg(), self.prob(), self.power_db(), self.active()
+            for b in range(self.info.n_streams):
+                for t in range(self.frames_done):
+                    if act[b, t]:                                           # _ptrCallback->setDOA(toDegrees(_currentDOA,1), _prob, power, 1)  (:245)
+                        self._callback(doa[b, t:t + 1], prob[b, t:t + 1], float(power[b, t]), 1)
+        return y
 
 
 class FastBinauralMasking(Processor):

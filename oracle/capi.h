@@ -47,6 +47,13 @@ int ORC_FN(freqgcc_run)(int fs, double mic_dist, int use_floor, int noise_preest
 /* setProbability on a given curve — BinauralLocalisation.cpp:569-631 */
 void ORC_FN(freqgcc_probability)(int fs, double mic_dist, const double *curve, const double *doas, double *probs, int size);
 
+/* MultibandBinarualLocalisation (MultibandBinarualLocalisation.cpp:52-259): per fired frame f the cell = arg-max of the energy-weighted
+ * DOA histogram, prob, power, doa_deg (the published _currentDOA), hist[f][D] = _energyInDOA, band_cells[f][nbins] = per-band arg-max
+ * cells.  noise_preestimated as for freqgcc_run (the same falling-off-the-end setPowerFloor wrapper, :115-124). Returns N; *n_dirs = D. */
+int ORC_FN(multiband_run)(int fs, double mic_dist, int nbins, int use_floor, int noise_preestimated, const double *in, int n, int chunk,
+                          int max_frames, int *n_frames, int *n_fired, int *fired_frame, int *n_dirs,
+                          int *cell, double *prob, double *power, double *doa_deg, double *hist, int *band_cells);
+
 /* FastBinauralMasking: Q[f][45] = short-time power after frame f; spectra_out[f][2][ccs] masked spectra (optional). */
 int ORC_FN(mask_run)(int fs, double mic_dist, float lo, float hi, int method, int alg,
                      const double *in, int n, int chunk, double *out, int out_cap, int *n_out,

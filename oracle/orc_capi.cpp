@@ -117,6 +117,56 @@ int orc_freqgcc_run(int fs, double mic_dist, int use_floor, int noise_preestimat
   return 1 << order;
 }
 
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct MbRun { MultibandState st; int frame = 0, fired = 0, max_frames = 0; int *fired_frame, *cell, *band_cells; double *prob, *power, *doa_deg, *hist; };
+void mb_hook(void *user, double *frames, int, int) {
+  MbRun &r = *static_cast<MbRun *>(user);
+  std::vector<double> hist(static_cast<size_t>(r.st.D)); std::vector<int> bc(static_cast<size_t>(r.st.nb)); int cell = 0;
+  FrameReport rep = multiband_frame(r.st, frames, hist.data(), bc.data(), &cell);
+  if (rep.fired && r.fired < r.max_frames) {
+    const int f = r.fired;
+    r.fired_frame[f] = r.frame; r.cell[f] = cell; r.prob[f] = r.st.prob; r.power[f] = rep.power;
+    r.doa_deg[f] = r.st.cur_doa * (180 / M_PI);
+    std::copy(hist.begin(), hist.end(), r.hist + size_t(f) * r.st.D);
+    std::copy(bc.begin(), bc.end(), r.band_cells + size_t(f) * r.st.nb);
+  }
+  if (rep.fired) ++r.fired;
+  ++r.frame;
+}
+}  // namespace
+
+int orc_multiband_run(int fs, double mic_dist, int nbins, int use_floor, int noise_preestimated, const double *in, int n, int chunk,
+                      int max_frames, int *n_frames, int *n_fired, int *fired_frame, int *n_dirs,
+                      int *cell, double *prob, double *power, double *doa_deg, double *hist, int *band_cells) {
+  const int order = dsp::ShortTimeProcess::calculateOrderFromSampleRate(fs, 0.025f);     // _frameRate, MultibandBinarualLocalisation.h:41
+  MbRun r;
+  r.st.init(fs, mic_dist, 1 << order, nbins, use_floor != 0);
+  if (n_dirs) *n_dirs = r.st.D;
+  if (!in) return 1 << order;
+  if (noise_preestimated) r.st.noise_estimated = true;
+  r.max_frames = max_frames; r.fired_frame = fired_frame; r.cell = cell; r.band_cells = band_cells; r.prob = prob; r.power = power; r.doa_deg = doa_deg; r.hist = hist;
+  FrameTap tap(2, order, false, mb_hook, &r);
+  feed(tap, 2, in, n, chunk, nullptr, 0, false);
+  if (n_frames) *n_frames = r.frame;
+  if (n_fired) *n_fired = r.fired;
+  return 1 << order;
+}
+
+// frame-level entry for the GPU tests: T spectra [T][2][N+2] from a fresh state (floor pre-estimated, gate off)
+extern "C" int orc_multiband_frames(const double *spec, int T, int N, int fs, double mic_dist, int nbins, int *cell, double *prob, double *hist,
+                                    int *band_cells, double *H_out /*[nbins][N/2+1] or NULL*/) {
+  MultibandState st;
+  st.init(fs, mic_dist, N, nbins, false);
+  st.noise_estimated = true;
+  if (H_out) std::copy(st.H.begin(), st.H.end(), H_out);
+  for (int t = 0; t < T && spec; ++t) {
+    multiband_frame(st, spec + size_t(t) * 2 * (N + 2), hist + size_t(t) * st.D, band_cells + size_t(t) * nbins, cell + t);
+    prob[t] = st.prob;
+  }
+  return st.D;
+}
+
 void orc_freqgcc_probability(int, double, const double *curve, const double *doas, double *probs, int size) {
   const float step = float(3 * M_PI / 180);
   freqgcc_probability(curve, num_doa_steps(step), step, doas, probs, size);

@@ -121,6 +121,38 @@ def freqgcc_run(fs, mic_dist, x, chunk=0, use_floor=False, noise_preestimated=Tr
                 idx=idx[:f].copy(), power=power[:f].copy())
 
 
+def multiband_run(fs, mic_dist, x, nbins=15, chunk=0, use_floor=False, noise_preestimated=True, prefix="orc"):
+    """MultibandBinarualLocalisation (MultibandBinarualLocalisation.cpp:52-259) over a whole stereo signal."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n = x.shape[1]
+    fn = getattr(lib(prefix), f"{prefix}_multiband_run")
+    D = C.c_int(0)
+    N = fn(C.c_int(fs), C.c_double(mic_dist), C.c_int(nbins), 0, 1, None, 0, 0, 0, None, None, None, C.byref(D), None, None, None, None, None, None)
+    D = D.value
+    maxf = max(1, n // (N // 2) + 2)
+    n_frames, n_fired = C.c_int(0), C.c_int(0)
+    fired_frame = np.zeros(maxf, dtype=np.int32); cell = np.zeros(maxf, dtype=np.int32); band_cells = np.zeros((maxf, nbins), dtype=np.int32)
+    prob = np.zeros(maxf); power = np.zeros(maxf); doa_deg = np.zeros(maxf); hist = np.zeros((maxf, D))
+    Dd = C.c_int(0)
+    r = fn(C.c_int(fs), C.c_double(mic_dist), C.c_int(nbins), C.c_int(int(use_floor)), C.c_int(int(noise_preestimated)), _dp(x), C.c_int(n),
+           C.c_int(chunk), C.c_int(maxf), C.byref(n_frames), C.byref(n_fired), _ip(fired_frame), C.byref(Dd), _ip(cell), _dp(prob), _dp(power),
+           _dp(doa_deg), _dp(hist), _ip(band_cells))
+    f = n_fired.value
+    return dict(N=r, D=D, n_frames=n_frames.value, n_fired=f, fired_frame=fired_frame[:f].copy(), cell=cell[:f].copy(), prob=prob[:f].copy(),
+                power=power[:f].copy(), doa_deg=doa_deg[:f].copy(), hist=hist[:f].copy(), band_cells=band_cells[:f].copy())
+
+
+def multiband_frames(spec, N, fs, mic_dist, nbins=15):
+    """frame-level restatement on given spectra [T][2][K] (fresh state, gate off): cells, prob, histogram, per-band cells, H"""
+    s = _ccs(spec); T = s.shape[0]
+    H = np.zeros((nbins, N // 2 + 1))
+    D = lib().orc_multiband_frames(None, 0, C.c_int(N), C.c_int(fs), C.c_double(mic_dist), C.c_int(nbins), None, None, None, None, _dp(H))
+    cell = np.zeros(T, dtype=np.int32); prob = np.zeros(T); hist = np.zeros((T, D)); bc = np.zeros((T, nbins), dtype=np.int32)
+    lib().orc_multiband_frames(_dp(s), C.c_int(T), C.c_int(N), C.c_int(fs), C.c_double(mic_dist), C.c_int(nbins), _ip(cell), _dp(prob), _dp(hist),
+                               _ip(bc), None)
+    return dict(cell=cell, prob=prob, hist=hist, band_cells=bc, H=H, D=D)
+
+
 def freqgcc_probability(fs, mic_dist, curve, doas, prefix="orc"):
     curve = np.ascontiguousarray(curve, dtype=np.float64); doas = np.ascontiguousarray(doas, dtype=np.float64)
     probs = np.zeros(len(doas))

@@ -11,6 +11,7 @@
 #include <mcarray/Beamformer.h>
 #include <mcarray/BinauralLocalisation.h>
 #include <mcarray/FastBinauralMasking.h>
+#include <mcarray/MultibandBinarualLocalisation.h>
 #include <mcarray/SoundLocalisationCallback.h>
 #include <mcarray/SourceLocalisation.h>
 #include <mcarray/SourceSeparationAndLocalisation.h>
@@ -170,6 +171,50 @@ void ref_freqgcc_probability(int fs, double mic_dist, const double *curve, const
   FreqGCCBinauralLocalisation p(fs, ArrayDescription::make_linear_array_description(x), false);
   std::copy(curve, curve + p._numSteps, p._correlationsReal.get());
   p.setProbability(doas, probs, size);
+}
+
+namespace {
+struct CountingMultiband : public MultibandBinarualLocalisation {
+  CountingMultiband(int fs, ArrayDescription a, int nbins, bool floor) : MultibandBinarualLocalisation(fs, a, nbins, floor), frames(0) {}
+  virtual void processParametrisation(std::vector<double *> &af, int al, std::vector<double *> &dc, int dl) {
+    MultibandBinarualLocalisation::processParametrisation(af, al, dc, dl);
+    ++frames;
+  }
+  int frames;
+};
+struct MultibandCapture : public LocalisationCallback {
+  CountingMultiband *proc; int fired, max_frames; int *fired_frame, *cell, *band_cells; double *prob, *power, *doa_deg, *hist;
+  virtual void setDOA(SignalPtr doa, SignalPtr p, double pw, int) {
+    if (fired < max_frames) {
+      const int D = proc->_numSteps, nb = proc->_numberOfBins;
+      fired_frame[fired] = proc->frames; power[fired] = pw; prob[fired] = p[0]; doa_deg[fired] = doa[0];
+      std::copy(proc->_energyInDOA.get(), proc->_energyInDOA.get() + D, hist + size_t(fired) * D);
+      double mx; size_t mi;
+      wipp::maxidx(proc->_energyInDOA.get(), size_t(D), &mx, &mi);                                   // :223
+      cell[fired] = int(mi);
+      for (int b = 0; b < nb; ++b)   // _binDOAs holds doaIdx2angle(idx) (:182): back to the cell
+        band_cells[size_t(fired) * nb + b] = int(std::lround((proc->_binDOAs[b] + M_PI_2) / double(proc->_doaStep)));
+    }
+    ++fired;
+  }
+};
+}  // namespace
+
+int ref_multiband_run(int fs, double mic_dist, int nbins, int use_floor, int noise_preestimated, const double *in, int n, int chunk,
+                      int max_frames, int *n_frames, int *n_fired, int *fired_frame, int *n_dirs,
+                      int *cell, double *prob, double *power, double *doa_deg, double *hist, int *band_cells) {
+  std::vector<double> x = {0.0, mic_dist};
+  CountingMultiband p(fs, ArrayDescription::make_linear_array_description(x), nbins, use_floor != 0);
+  if (n_dirs) *n_dirs = p._numSteps;
+  if (!in) return p.getWindowSize();
+  if (noise_preestimated) p._noiseEstimated = true;
+  MultibandCapture cb; cb.proc = &p; cb.fired = 0; cb.max_frames = max_frames; cb.fired_frame = fired_frame; cb.cell = cell; cb.band_cells = band_cells;
+  cb.prob = prob; cb.power = power; cb.doa_deg = doa_deg; cb.hist = hist;
+  p.setCallback(&cb);
+  feed(p, 2, in, n, chunk, nullptr, 0, false);
+  if (n_frames) *n_frames = p.frames;
+  if (n_fired) *n_fired = cb.fired;
+  return p.getWindowSize();
 }
 
 namespace {

@@ -343,6 +343,88 @@ inline void freqgcc_probability(const double *curve, int D, float doa_step, cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// N2 — MultibandBinarualLocalisation, MultibandBinarualLocalisation.cpp:52-259: per linear sub-band a
+// GCC-PHAT curve on the 5-degree grid with 0.4 memory and its arg-max, then an energy-weighted histogram of the band
+// arg-maxima whose own arg-max is the published DOA.  The sub-band frames are X * H_b (stand-in C8).
+// ------------------------------------------------------------------------------------------------
+struct MultibandState {
+  int fs, N, K, D, nb; float doa_step; bool use_floor;
+  double mic_dist;
+  std::vector<double> tau, H /*[nb][K]*/, prev_corr /*[nb][D]*/;
+  double cur_doa, prob, power_floor; bool noise_estimated; int samples_for_noise;
+  void init(int fs_, double mic_dist_, int N_, int nbins, bool use_floor_) {
+    fs = fs_; N = N_; K = N / 2 + 1; nb = nbins; use_floor = use_floor_; mic_dist = mic_dist_;
+    doa_step = float(5 * M_PI / 180);                                                      // :62
+    D = int(std::floor(M_PI / doa_step) + 1);                                              // :63 (floor here, round in SteeringBeamforming)
+    tau.resize(size_t(D));
+    for (int i = 0; i < D; ++i) tau[size_t(i)] = doa_to_delay_far_field_samples(doa_idx_to_angle(i, doa_step), float(mic_dist), fs);   // :99
+    int order = 0; while ((1 << order) < N) ++order;
+    const float max_freq = float(speed_of_sound() / (2 * float(mic_dist)));                // maxFreqForSpatialAliasing, microhponeArrayHelpers.cpp:85-89
+    dsp::FilterBankFFTWLinear bank(order, nb, fs, 100, max_freq);                          // :54-60
+    H.assign(bank.band(0), bank.band(0) + size_t(nb) * K);
+    prev_corr.assign(size_t(nb) * D, 0.0);
+    cur_doa = 0; prob = -1; power_floor = 0; noise_estimated = false; samples_for_noise = 0;   // :76-79, SoundLocalisationImpl
+  }
+};
+
+// frames [2][N+2].  hist_out [D] = _energyInDOA, band_cells_out [nb], *cell_out = arg-max of the histogram.
+inline FrameReport multiband_frame(MultibandState &st, const double *frames, double *hist_out, int *band_cells_out, int *cell_out) {
+  const int ccs = 2 * st.K;
+  std::vector<double> hist(size_t(st.D), 0.0), band(size_t(2) * ccs), c(size_t(st.D));    // processSetup :145-151
+  const float mem = 0.4f;                                                                  // _corrMemoryFactor, .h:44
+  for (int b = 0; b < st.nb; ++b) {                                                        // processOneSubband :164-196
+    const double *h = &st.H[size_t(b) * st.K];
+    for (int ch = 0; ch < 2; ++ch)
+      for (int i = 0; i < ccs; ++i) band[size_t(ch) * ccs + i] = frames[size_t(ch) * ccs + i] * h[i / 2];
+    gcc_phat_tau(band.data(), band.data() + ccs, st.K, st.tau.data(), st.D, c.data());    // :175-179
+    double *prev = &st.prev_corr[size_t(b) * st.D];
+    for (int d = 0; d < st.D; ++d) {                                                       // :180-183
+      c[size_t(d)] *= double(1 - mem);
+      prev[d] *= double(mem);
+      c[size_t(d)] += prev[d];
+      prev[d] = c[size_t(d)];
+    }
+    double mx; size_t mi;
+    wipp::maxidx(c.data(), size_t(st.D), &mx, &mi);                                        // :184
+    std::vector<const double *> bv{band.data(), band.data() + ccs};
+    hist[mi] += dsp::SignalPower::FFTPower(bv, ccs);                                       // :188-190
+    if (band_cells_out) band_cells_out[b] = int(mi);
+  }
+  std::vector<const double *> fv{frames, frames + ccs};
+  double power;
+  if (!st.noise_estimated) {                                                               // :214-217 -> :127-143
+    const int K = ccs / 2, needed = int(3 * st.fs);
+    st.power_floor += dsp::SignalPower::FFTPower(fv, K) * (2 * K - 2);
+    st.samples_for_noise += (2 * K - 2);
+    if (st.samples_for_noise >= needed) {
+      st.noise_estimated = true;
+      st.power_floor /= st.samples_for_noise;
+      st.power_floor = 10 * std::log10(st.power_floor) + double(3.0f);
+    }
+    power = st.power_floor;
+  } else {
+    power = dsp::SignalPower::FFTPower(fv, ccs);                                           // :221
+  }
+  FrameReport r; r.power = power; r.fired = false;
+  if (power > st.power_floor || !st.use_floor) {                                           // :225
+    double sum = 0, mx; size_t mi;
+    wipp::sum(hist.data(), size_t(st.D), &sum);
+    wipp::maxidx(hist.data(), size_t(st.D), &mx, &mi);
+    st.prob = sum;
+    if (st.prob != 0) st.prob = hist[mi] / st.prob;                                        // :230-233
+    const double doa = doa_idx_to_angle(int(mi), st.doa_step);
+    st.cur_doa = double(0.0f) * st.cur_doa + double(1 - 0.0f) * doa;                       // _doaMemoryFactor = 0 (:239)
+    if (cell_out) *cell_out = int(mi);
+    r.fired = true;
+  } else {
+    st.cur_doa = st.cur_doa * double(1.0f) + double(1 - 1.0f) * 0;                         // :252
+    st.prob = -100000;
+  }
+  if (hist_out) std::copy(hist.begin(), hist.end(), hist_out);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
 // A10 — FastBinauralMasking, FastBinauralMasking.cpp:51-538; constants FastBinauralMasking.h:111-128.
 // ------------------------------------------------------------------------------------------------
 enum MaskMethod { M_FACTOR = 0, M_RELATIVE = 1, M_FULL = 3, M_NOISY = 4, M_NOTHING = 5 };   // ArrayModules.h:81

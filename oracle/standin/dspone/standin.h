@@ -18,6 +18,7 @@
 
 #include <wipp/wipp.h>
 #include <boost/shared_array.hpp>
+#include <boost/scoped_ptr.hpp>
 
 #include <cmath>
 #include <complex>
@@ -413,6 +414,80 @@ class FilterBankFFTWMelScale : public FilterBank {
  private:
   int _nBins, _K, _fs;
   std::vector<double> _coefs, _centres;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Linear filter bank + SubBandSTFTAnalysis (C8).  Call site: MultibandBinarualLocalisation.cpp:52-60
+// (ctor `SubBandSTFTAnalysis(nbins, fs, order, 2, 100, maxFreq, SubBandSTFT::LINEAR)`), hooks
+// processSetup / processOneSubband(frame, length, bin) / processSumamry (:145-259).
+// Stand-in semantics: the bank has nbins triangular magnitude responses with unit peak whose centres
+// are equally spaced in Hz between minFreq and maxFreq (same shape rule as the mel bank, linear axis);
+// per frame the hooks see, for every band, the CCS spectra of all channels multiplied by that band's
+// real response (a frequency-domain filter bank, like FastBinauralMasking.cpp:148-153 applies its own).
+// ------------------------------------------------------------------------------------------------
+class FilterBankFFTWLinear : public FilterBank {
+ public:
+  FilterBankFFTWLinear(int order, int nBins, int sampleRate, float minFreq, float maxFreq)
+      : _nBins(nBins), _K((1 << (order - 1)) + 1) {
+    const int N = 1 << order;
+    std::vector<double> edges(size_t(nBins) + 2);
+    for (int i = 0; i < nBins + 2; ++i) edges[size_t(i)] = double(minFreq) + (double(maxFreq) - double(minFreq)) * double(i) / double(nBins + 1);
+    _coefs.assign(size_t(nBins) * size_t(_K), 0.0);
+    _centres.resize(size_t(nBins));
+    for (int b = 0; b < nBins; ++b) {
+      const double lo = edges[size_t(b)], mid = edges[size_t(b) + 1], hi = edges[size_t(b) + 2];
+      _centres[size_t(b)] = mid / double(sampleRate);
+      for (int k = 0; k < _K; ++k) {
+        const double f = double(k) * double(sampleRate) / double(N);
+        double v = 0.0;
+        if (f > lo && f <= mid) v = (f - lo) / (mid - lo);
+        else if (f > mid && f < hi) v = (hi - f) / (hi - mid);
+        _coefs[size_t(b) * size_t(_K) + size_t(k)] = v;
+      }
+    }
+  }
+  virtual int getFiltersCoeficients(double *coefs, int length) const {
+    int n = std::min(length, int(_coefs.size()));
+    for (int i = 0; i < n; ++i) coefs[i] = _coefs[size_t(i)];
+    return int(_coefs.size());
+  }
+  virtual double getBinCenterFrequency(int bin) const { return _centres[size_t(bin)]; }
+  int getNBins() const { return _nBins; }
+  const double *band(int b) const { return &_coefs[size_t(b) * size_t(_K)]; }
+ private:
+  int _nBins, _K;
+  std::vector<double> _coefs, _centres;
+};
+
+class SubBandSTFT { public: typedef enum { LINEAR = 0, MEL = 1 } BandScale; };
+
+class SubBandSTFTAnalysis : public STFTAnalysis {
+ public:
+  SubBandSTFTAnalysis(int nbins, int sampleRate, int order, int nchannels, float minFreq, float maxFreq, SubBandSTFT::BandScale)
+      : STFTAnalysis(nchannels, order), _filterBank(new FilterBankFFTWLinear(order, nbins, sampleRate, minFreq, maxFreq)), _nSubBands(nbins) {
+    for (int c = 0; c < nchannels; ++c) _bandStore.push_back(std::vector<double>(size_t(_analysisLength), 0.0));
+  }
+  int getNumberOfBins() const { return _nSubBands; }
+ protected:
+  virtual void processSetup(std::vector<double *> &analysisFrames, int analysisLength, std::vector<double *> &dataChannels, int dataLength) = 0;
+  virtual void processOneSubband(std::vector<double *> &analysisFrame, int length, int bin) = 0;
+  virtual void processSumamry(std::vector<double *> &analysisFrames, int analysisLength, std::vector<double *> &dataChannels, int dataLength) = 0;
+  virtual void processParametrisation(std::vector<double *> &analysisFrames, int analysisLength, std::vector<double *> &dataChannels, int dataLength) {
+    processSetup(analysisFrames, analysisLength, dataChannels, dataLength);
+    std::vector<double *> band;
+    for (size_t c = 0; c < analysisFrames.size(); ++c) band.push_back(_bandStore[c].data());
+    for (int b = 0; b < _nSubBands; ++b) {
+      const double *h = _filterBank->band(b);
+      for (size_t c = 0; c < analysisFrames.size(); ++c)
+        for (int i = 0; i < analysisLength; ++i) band[c][i] = analysisFrames[c][i] * h[i / 2];
+      processOneSubband(band, analysisLength, b);
+    }
+    processSumamry(analysisFrames, analysisLength, dataChannels, dataLength);
+  }
+  boost::scoped_ptr<FilterBankFFTWLinear> _filterBank;
+ private:
+  int _nSubBands;
+  std::vector<std::vector<double>> _bandStore;
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -105,6 +105,30 @@ static int runSsl(int argc, char **argv) {
   return g_failures ? 1 : 0;
 }
 
+// MultibandBinarualLocalisation (N2) on a planar stereo signal: one line per callback
+static int runMultiband(int argc, char **argv) {
+  if (argc < 8) return 64;
+  const int n = std::atoi(argv[3]), fs = std::atoi(argv[4]), chunk = std::atoi(argv[6]);
+  const double dist = std::atof(argv[5]);
+  std::vector<double> x(size_t(2) * n);
+  std::ifstream f(argv[2], std::ios::binary);
+  f.read(reinterpret_cast<char *>(x.data()), std::streamsize(x.size() * 8));
+  if (!f) { std::cerr << "short read" << std::endl; return 65; }
+  ArrayDescription array = ArrayDescription::make_linear_array_description(std::vector<double>{0.0, dist});
+  MultibandBinarualLocalisation mbl(fs, array, 15, false);
+  EXPECT(mbl.getNumberOfBins() == 15 && mbl.getWindowSize() == 512);
+  std::ofstream doa(std::string(argv[7]) + ".doa");
+  RecordingCallback cb(doa);
+  mbl.setCallback(cb);
+  std::vector<double *> rin(2);
+  for (int pos = 0; pos < n; pos += chunk) {
+    for (int c = 0; c < 2; ++c) rin[c] = x.data() + size_t(c) * n + pos;
+    mbl.process(rin, std::min(chunk, n - pos));
+  }
+  std::cout << "frames with callbacks: " << cb.count << std::endl;
+  return g_failures ? 1 : 0;
+}
+
 // plane wave from grid cell `cell` on a linear array: X_c[k] = S[k] exp(+j 2 pi k fs/N x_c sin(theta)/c)
 static int runFrame(int argc, char **argv) {
   const int fs = argc > 2 ? std::atoi(argv[2]) : 16000, N = argc > 3 ? std::atoi(argv[3]) : 512, ccs = N + 2, K = N / 2 + 1;
@@ -153,6 +177,7 @@ int main(int argc, char **argv) {
     if (mode == "array") { testArrayDescription(); std::cout << (g_failures ? "FAILED" : "testArrayDescription ok") << std::endl; return g_failures ? 1 : 0; }
     if (mode == "ssl") return runSsl(argc, argv);
     if (mode == "frame") return runFrame(argc, argv);
+    if (mode == "multiband") return runMultiband(argc, argv);
   } catch (const std::exception &e) {
     std::cerr << "exception: " << e.what() << std::endl;
     return 3;

@@ -50,6 +50,17 @@ def main():
     r = orc.freqgcc_run(fs, 0.086, x, chunk=2048, prefix="ref")
     np.savez_compressed(os.path.join(HERE, "freqgcc_16k.npz"), fs=fs, mic_dist=0.086, x=x.astype(np.int16), chunk=2048,
                         curves=r["curves"], idx=r["idx"], power=r["power"], N=r["N"])
+    # 3b. MultibandBinarualLocalisation, 0.086 m, 15 linear bands; source moves from +35 to -20 degrees half way
+    fs = 16000
+    xyz = scenes.linear_array([0, 0.086])
+    n = 30 * 256 + 512
+    xa = scenes.far_field_scene(xyz, fs, n, scenes.azimuth_dirs([np.deg2rad(35)]), seed=105)
+    xb = scenes.far_field_scene(xyz, fs, n, scenes.azimuth_dirs([np.deg2rad(-20)]), seed=106)
+    x = np.round(np.concatenate([xa, xb], axis=1))
+    r = orc.multiband_run(fs, 0.086, x, nbins=15, chunk=3000, prefix="ref")
+    np.savez_compressed(os.path.join(HERE, "multiband_16k.npz"), fs=fs, mic_dist=0.086, nbins=15, x=x.astype(np.int16), chunk=3000,
+                        cell=r["cell"], prob=r["prob"], power=r["power"], doa_deg=r["doa_deg"], hist=r["hist"], band_cells=r["band_cells"],
+                        fired_frame=r["fired_frame"], N=r["N"], D=r["D"])
     # 4. FastBinauralMasking on the reference's spatial-masking test signal (test_mcarray.cpp:908-929)
     n = 5 * 1024
     i = np.arange(n)

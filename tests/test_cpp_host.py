@@ -91,6 +91,24 @@ def test_cpp_ssl_against_reference_golden(tools, tmp_path):
 
 
 @pytest.mark.gpu
+def test_cpp_multiband_against_reference_golden(tools, tmp_path):
+    """mca::MultibandBinarualLocalisation (C++ host class over the C ABI) against the reference fixture: one callback per frame,
+    published DOA in degrees"""
+    g = np.load(os.path.join(G, "multiband_16k.npz"))
+    x = g["x"].astype(np.float64)
+    x.tofile(tmp_path / "in.f64")
+    r = subprocess.run([os.path.join(tools, "test_mcarray_api"), "multiband", str(tmp_path / "in.f64"), str(x.shape[1]), str(int(g["fs"])),
+                        repr(float(g["mic_dist"])), str(int(g["chunk"])), str(tmp_path / "res")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rows = np.loadtxt(tmp_path / "res.doa").reshape(-1, 3)
+    # the reference would not fire during its first 3 s (floor estimation with the gate off fires every frame: power > floor is not
+    # required when usePowerFloor is false), so every frame is delivered
+    assert rows.shape[0] == g["doa_deg"].shape[0]
+    assert np.allclose(rows[:, 0], g["doa_deg"], atol=1e-5)
+    assert np.allclose(rows[:, 1], g["prob"], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.gpu
 def test_mcbeam_cli_against_reference_golden(tools, tmp_path):
     """mcbeam -i in.wav -o out.wav -d doa.txt on the reference CLI's own hard-coded array (mcabeamf.cpp:182)."""
     g = np.load(os.path.join(G, "ssl_mcbeam_48k.npz"))

@@ -209,6 +209,59 @@ def test_freqgcc_against_reference_golden(mb):
     assert_close(curves, g["curves"], (1,), "smoothed GCC curve")
 
 
+def test_multiband_against_reference_golden(mb):
+    """N2 MultibandBinarualLocalisation against the fixture produced by the reference's own MultibandBinarualLocalisation.cpp:
+    published cells and per-band arg-max cells bit-exact, histogram / prob within tolerance, callback deliveries in order."""
+    g = np.load(os.path.join(G, "multiband_16k.npz"))
+    x = g["x"].astype(np.float32)
+    p = mb.MultibandBinarualLocalisation(int(g["fs"]), float(g["mic_dist"]), nbins=int(g["nbins"]), usePowerFloor=False, max_frames_per_call=64,
+                                         noise_preestimated=True)
+    assert p.info.n_dirs == int(g["D"]) and p.info.window_size == int(g["N"])
+    fired = []
+    p.setCallback(lambda doa, prob, power, n: fired.append((float(doa[0]), float(prob[0]), power)))
+    cells, bcells, hist, prob = [], [], [], []
+    for pos in range(0, x.shape[1], int(g["chunk"])):
+        p.process(x[:, pos:pos + int(g["chunk"])])
+        if p.frames_done:
+            cells.append(p.cells()[0]); bcells.append(p.band_cells()[0]); hist.append(p.histogram()[0]); prob.append(p.prob()[0])
+    cells = np.concatenate(cells); bcells = np.concatenate(bcells); hist = np.concatenate(hist); prob = np.concatenate(prob)
+    assert np.array_equal(cells, g["cell"]), f"{np.sum(cells != g['cell'])} published cells differ"
+    assert np.array_equal(bcells, g["band_cells"]), f"{np.sum(bcells != g['band_cells'])} band cells differ"
+    assert_close(hist, g["hist"], (1,), "energy-weighted DOA histogram")
+    assert np.allclose(prob, g["prob"], rtol=1e-4, atol=1e-6)
+    assert len(fired) == len(g["cell"])
+    assert np.allclose([f[0] for f in fired], g["doa_deg"], atol=1e-5)
+    assert np.allclose([f[2] for f in fired], g["power"], rtol=1e-4)
+
+
+def test_multiband_gate_and_streams_vs_oracle(mb, orc):
+    """power gate (floor estimated on a quiet lead-in), several streams in one handle, chunked calls: fired frames, cells and
+    band cells must match the oracle run of each stream"""
+    fs, d, B = 16000, 0.089, 3
+    xyz = scenes.linear_array([0, d])
+    xs = []
+    for b in range(B):
+        x = scenes.far_field_scene(xyz, fs, 4 * fs + 1000, scenes.azimuth_dirs([np.deg2rad(-50 + 40 * b)]), seed=scenes.stream_seed(40 + b))
+        x[:, : 3 * fs + 3000] *= 1e-3
+        xs.append(np.round(x * 4))
+    X = np.stack(xs).astype(np.float32)
+    p = mb.MultibandBinarualLocalisation(fs, d, nbins=15, usePowerFloor=True, n_streams=B, max_frames_per_call=64)
+    act, cells, bcells = [], [], []
+    flat = X.reshape(B * 2, -1)
+    for pos in range(0, flat.shape[1], 5000):
+        p.process(flat[:, pos:pos + 5000])
+        if p.frames_done:
+            act.append(p.active()); cells.append(p.cells()); bcells.append(p.band_cells())
+    act = np.concatenate(act, axis=1); cells = np.concatenate(cells, axis=1); bcells = np.concatenate(bcells, axis=1)
+    for b in range(B):
+        ref = orc.multiband_run(fs, d, X[b].astype(np.float64), nbins=15, chunk=5000, use_floor=True, noise_preestimated=False)
+        on = act[b].astype(bool)
+        assert 0 < ref["n_fired"] < ref["n_frames"]
+        assert np.array_equal(np.nonzero(on)[0], ref["fired_frame"]), "gate decisions differ"
+        assert np.array_equal(cells[b][on], ref["cell"])
+        assert np.array_equal(bcells[b][on], ref["band_cells"])
+
+
 @pytest.mark.parametrize("name,method", [("full", "FULL"), ("relative", "RELATIVE"), ("factor", "FACTOR"), ("noisy", "NOISY")])
 def test_mask_against_reference_golden(mb, name, method):
     g = np.load(os.path.join(G, "mask_spatial_16k.npz"))

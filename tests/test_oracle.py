@@ -136,3 +136,14 @@ def test_select_doa_edge_cases(orc):
     e = (np.maximum(0, 5 - np.abs(d - 10)) + 1.8 * np.maximum(0, 5 - np.abs(d - 25)))[None, :]
     idx, prob = orc.select_doa(e, 6, 3)
     assert idx[0, 0] == 25 and idx[0, 1] == 10 and prob[0, 0] > prob[0, 1] > 0 and prob[0, 2] == 0
+
+
+def test_multiband_golden(orc):
+    """the restatement reproduces the committed reference fixture (so the oracle is pinned on the GPU box too)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "multiband_16k.npz"))
+    r = orc.multiband_run(int(g["fs"]), float(g["mic_dist"]), g["x"].astype(np.float64), nbins=int(g["nbins"]), chunk=int(g["chunk"]))
+    for k in ("cell", "prob", "power", "doa_deg", "hist", "band_cells", "fired_frame"):
+        assert np.array_equal(r[k], g[k]), k
+    # the source moves from +35 to -20 degrees: the published cells follow it (5 degree grid, cell = (deg + 90) / 5)
+    assert np.median(g["cell"][5:25]) == 25 and np.median(g["cell"][-20:]) == 14

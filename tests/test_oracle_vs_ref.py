@@ -93,3 +93,17 @@ def test_helpers_and_frames_bit_exact(orc):
         assert np.array_equal(orc.beamformer_frame(48000, xyz, fr[0], doa), orc.beamformer_frame(48000, xyz, fr[0], doa, "ref"))
     a = orc.steering_frames(48000, xyz, fr, 3); b = orc.steering_frames(48000, xyz, fr, 3, "ref")
     _eq(a, b, ["doa_rad", "prob", "energy"])
+
+
+def test_multiband_bit_exact(orc):
+    """N2: MultibandBinarualLocalisation restatement against the reference's own MultibandBinarualLocalisation.cpp."""
+    fs = 16000
+    xyz = scenes.linear_array([0, 0.089])  # test_mcarray.cpp:325
+    x = scenes.far_field_scene(xyz, fs, 2 * fs, scenes.azimuth_dirs([np.deg2rad(40)]), seed=3)
+    x[:, fs:] *= 1e-4                       # near silence (the reference compares a LINEAR power with its dB floor, :221-225)
+    for nbins, floor in ((15, False), (8, True)):
+        a = orc.multiband_run(fs, 0.089, x, nbins=nbins, chunk=900, use_floor=floor)
+        b = orc.multiband_run(fs, 0.089, x, nbins=nbins, chunk=900, use_floor=floor, prefix="ref")
+        assert a["N"] == b["N"] == 512 and a["D"] == b["D"] == 37 and a["n_frames"] == b["n_frames"]
+        assert a["n_fired"] == b["n_fired"] > 0
+        _eq(a, b, ["fired_frame", "cell", "prob", "power", "doa_deg", "hist", "band_cells"])
