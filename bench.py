@@ -358,9 +358,10 @@ class ClockSampler:
     the nvidia-smi recipe in B200_PROFILING.md prints; nvidia-smi's 100 ms loop is too coarse for a tens-of-ms region)."""
     BITS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "hw_power_brake": 0x80}
 
-    def __init__(self, gpu_index, period=0.025):
-        # NVML queries take driver locks that kernel / NCCL launches also need: poll gently (25 ms), not in a tight loop
+    def __init__(self, gpu_index, period=0.010):
+        # NVML queries take driver locks that kernel / NCCL launches also need: poll gently (10 ms), not in a tight loop
         self.gpu, self.rows, self._stop, self.thread, self.err, self.period = gpu_index, [], threading.Event(), None, None, period
+        self._ready, self._armed = threading.Event(), threading.Event()
 
     def _run(self):
         try:
@@ -370,6 +371,9 @@ class ClockSampler:
             idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
             h = nv.nvmlDeviceGetHandleByIndex(idx)
             mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)              # first query pays the lazy initialisation
+            self._ready.set()
+            self._armed.wait()                                          # samples are taken only inside the timed region
             while not self._stop.is_set():
                 self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), mx, nv.nvmlDeviceGetPowerUsage(h) / 1e3,
                                   nv.nvmlDeviceGetCurrentClocksEventReasons(h)))
@@ -377,21 +381,29 @@ class ClockSampler:
             nv.nvmlShutdown()
         except Exception as e:  # noqa: BLE001
             self.err = repr(e)
+            self._ready.set()
 
-    def start(self):
+    def prepare(self):
+        """start the thread and wait until NVML is initialised (outside the timed region)"""
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
-        time.sleep(0.05)
+        self._ready.wait(timeout=10)
+
+    def start(self):
+        if self.thread is None:
+            self.prepare()
+        self._armed.set()
 
     def stop(self):
         self._stop.set()
+        self._armed.set()
         self.thread.join(timeout=5)
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"no NVML samples ({self.err})"]}
         sm = [r[0] for r in self.rows]
         reasons = sorted({name for r in self.rows for name, bit in self.BITS.items() if r[3] & bit})
         return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(sm), "power_w_max": float(max(r[2] for r in self.rows)), "how": "NVML polled every ~25 ms during the timed region"}
+                "samples": len(sm), "power_w_max": float(max(r[2] for r in self.rows)), "how": "NVML polled every ~10 ms during the timed region"}
 
 
 def profile_read(p, reset=True):
@@ -522,6 +534,8 @@ def main():
     assert p.frames_done == T, (p.frames_done, T)
     capi.check(capi.lib().mcag_profile_enable(p.handle, 1)); profile_read(p)
     sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.prepare()
     launches0 = p.kernel_launches
     barrier()
     if sampler:
