@@ -127,7 +127,9 @@ __device__ __forceinline__ void fft_pass_store(float2 *v, fft_buf_t buf, const f
     if (NS > 1) {
 #pragma unroll
       for (int r = 1; r < R; ++r) {
-        float2 w = twp[(SLOT0 + b * (R - 1) + (r - 1)) * TPF + j];
+        // the factor depends on the thread only through k = j & (NS-1) when NS < TPF: lanes with the same k then read the SAME
+        // table entry (a broadcast: 8 distinct float2 per warp in the NS = 8 pass is one wavefront instead of two)
+        float2 w = twp[(SLOT0 + b * (R - 1) + (r - 1)) * TPF + (NS < TPF ? (j & (NS - 1)) : j)];
         if (INV) w.y = -w.y;
         u[r] = cmul(u[r], w);
       }
