@@ -461,6 +461,7 @@ def main():
     ap.add_argument("--cpu-streams-per-core", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-s16", action="store_true", help="also time the end-to-end path with int16 PCM host buffers (extra key e2e_s16)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3 if args.impl == "b200" else max(args.warmup, 1)
@@ -591,6 +592,34 @@ def main():
         e2e = {"value": units_job / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": input_bytes, "d2h_bytes_per_step": int(res_bytes),
                "ms_per_step": ms_e2e}
 
+    # ---- e2e with 16-bit PCM host buffers (the int16 overload of process(), test_mcarray.cpp:937): half the PCIe bytes ----------------
+    e2e_s16 = None
+    if not args.no_e2e and not sharded and args.e2e_s16:
+        pin16 = torch.empty((rows, n), dtype=torch.int16).pin_memory()
+        pin16.copy_(pin.round().clamp_(-32768, 32767).to(torch.int16))
+        in_ptrs = (C.POINTER(C.c_int16) * rows)(*[C.cast(pin16.data_ptr() + 2 * r * n, C.POINTER(C.c_int16)) for r in range(rows)])
+        out16, out_ptrs, orows = None, None, B * p.info.n_out_channels
+        if orows:
+            out16 = torch.empty((orows, T * wl.hop), dtype=torch.int16).pin_memory()
+            out_ptrs = (C.POINTER(C.c_int16) * orows)(*[C.cast(out16.data_ptr() + 2 * r * T * wl.hop, C.POINTER(C.c_int16)) for r in range(orows)])
+        nout16 = C.c_int(0)
+
+        def step_s16():
+            p.flush_input()
+            capi.check(capi.lib().mcag_process_s16(p.handle, in_ptrs, C.c_int(n), out_ptrs, C.c_int(T * wl.hop if orows else 0), C.byref(nout16)))
+            return wl.fetch_result(p)
+        for _ in range(args.warmup):
+            step_s16()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_s16()
+        p.synchronize()
+        ms16 = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+        barrier()
+        e2e_s16 = {"value": units_job / (ms16 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": rows * n * 2, "d2h_bytes_per_step": int(wl.result_bytes(p, B, T)),
+                   "ms_per_step": ms16, "note": "same samples rounded to int16 PCM through mcag_process_s16 (planar pinned host rows); timed by host clock around synchronous calls"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -629,9 +658,15 @@ def main():
                              "frac": wl.pipeline_bytes_per_frame() * B * T / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"]},
                 "kernels_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr):
+    if os.path.exists(tr):   # measured DRAM bytes of one launch of the dominant kernel + what ncu says binds it (committed captures)
         with open(tr) as f:
-            roofline["traffic"] = json.load(f).get(args.workload, {}).get(dom)
+            tj = json.load(f)
+        roofline["traffic"] = tj.get(args.workload, {}).get(dom)
+        lim = tj.get("_limiter", {}).get(args.workload, {}).get(dom)
+        if lim:
+            roofline["limiter"] = lim
+        if roofline["traffic"] is not None and (B, T) != (wl.B_default, wl.T_default):
+            roofline["traffic_note"] = "captured at the default streams / frames of this workload"
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -643,6 +678,8 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
     if e2e:
         line["e2e"] = e2e
+    if e2e_s16:
+        line["e2e_s16"] = e2e_s16
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = run_cpu(wl, args, rank, world, False)
     print(json.dumps(line), flush=True)
