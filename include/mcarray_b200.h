@@ -201,6 +201,9 @@ int mcag_k_select_doa(const float *d_energy, long long BT, int D, int n_pairs, i
  * ordered(E) << 31 | (0x7FFFFFFF - d): an int64 MAX all-reduce over the slices of a sharded grid gives the global arg-max cell */
 int mcag_k_argmax_pack(const float *d_map, long long rows, int D, int d_offset, long long *d_packed, void *stream);
 int mcag_k_ds_fan(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_steer_fx, int D, void *d_out, void *stream);
+/* the fan on the tensor cores (tcgen05, 3xTF32; M in {16, 32, 48, 64}, other counts run mcag_k_ds_fan).  Same results; measured 4x
+ * slower than mcag_k_ds_fan on B200 for the [B][T][D][K] beam layout (scattered 8-byte stores), so the processors do not use it. */
+int mcag_k_ds_fan_tensor(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_steer_fx, int D, void *d_out, void *stream);
 int mcag_k_srp_channel(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_mic_fx, int D, float *d_srp, void *stream);
 int mcag_k_srp_tensor(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_mic_fx, int D, float *d_srp, void *stream);
 

@@ -686,6 +686,8 @@ static int run_frames(mcag_proc p, const float *x_all, long long pitch, int T, i
     }
   } else if (kind == MCAG_KIND_DSFAN) {
     PROF(MCAG_PROF_DS_FAN);
+    // CUDA cores on purpose: the tcgen05 variant (mcag_k_ds_fan_tensor) is 4x slower here, because the bin index is the batch index of
+    // the contraction and a tile never holds consecutive bins of one beam (scattered 8-byte stores)
     OK(k_ds_fan(spec, B, T, M, N, p->steer_fx.as<uint64_t>(), D, p->beams.as<float2>() + o * T * D * KP, st));
     p->launches++;
   } else if (kind == MCAG_KIND_SRP) {

@@ -42,6 +42,10 @@ size_t k_srp_tensor_workspace_bytes(long long BT, int M, int N, int D);
 int k_srp_tensor_ws(const float2 *spec, int B, int T, int M, int N, const uint64_t *mic_fx, int D, float *srp, void *workspace, size_t ws_bytes,
                     cudaStream_t st);
 int k_srp_tensor(const float2 *spec, int B, int T, int M, int N, const uint64_t *mic_fx, int D, float *srp, cudaStream_t st);
+size_t k_ds_fan_tensor_workspace_bytes(long long BT, int M, int N);
+int k_ds_fan_tensor_ws(const float2 *spec, int B, int T, int M, int N, const uint64_t *steer_fx, int D, float2 *out, void *workspace, size_t ws_bytes,
+                       cudaStream_t st);
+int k_ds_fan_tensor(const float2 *spec, int B, int T, int M, int N, const uint64_t *steer_fx, int D, float2 *out, cudaStream_t st);
 
 // mask.cu
 int k_mask_stats(const float2 *spec, long long BT, int N, const float *H2, int nb, float *stats, cudaStream_t st);

@@ -109,6 +109,8 @@ __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__flo
 
 // ---- pre-pass: whiten, split, transpose to bin-major --------------------------------------------------------------------
 // spec [BT][M][KP] float2  ->  U_hi / U_lo [K][BTpad][2M] fp32 (rows t >= BT stay zero), nzsum[t] = sum_k #(non-zero channels)
+// WHITEN = false keeps the raw spectra (delay-and-sum fan): same layout, no PHAT, no non-zero count.
+template <bool WHITEN>
 __global__ void __launch_bounds__(256) srp_prepare_kernel(const float2 *__restrict__ spec, long long BT, long long BTpad, int M, int N,
                                                            float *__restrict__ Uhi, float *__restrict__ Ulo, float *__restrict__ nzsum) {
   __shared__ float2 s_t[32][65];   // [bin in chunk][mic], M <= 64
@@ -131,8 +133,11 @@ __global__ void __launch_bounds__(256) srp_prepare_kernel(const float2 *__restri
       const int k = k0 + lane;
       float2 u = make_float2(0.f, 0.f);
       if (k < K) {
-        u = whiten(spec[(t * M + m) * KP + k]);
-        nz += (u.x != 0.f || u.y != 0.f) ? 1.f : 0.f;
+        u = spec[(t * M + m) * KP + k];
+        if (WHITEN) {
+          u = whiten(u);
+          nz += (u.x != 0.f || u.y != 0.f) ? 1.f : 0.f;
+        }
       }
       s_t[lane][m] = u;
     }
@@ -149,6 +154,7 @@ __global__ void __launch_bounds__(256) srp_prepare_kernel(const float2 *__restri
     }
     __syncthreads();
   }
+  if (!WHITEN) return;
   nz = warp_sum(nz);
   if (lane == 0) s_nz[warp] = nz;
   __syncthreads();
@@ -166,10 +172,15 @@ struct TcParams {
   int n_tt, n_dt, n_ks;  // frame tiles, direction tiles, bin ranges
   int bins_per_range;
   const uint64_t *mic_fx;   // [D][M] 0.64 fixed-point turns per bin
-  float *partial;           // [n_ks][BT][D]
+  float *partial;           // [n_ks][BT][D]                      (SRP: partial energy maps)
+  float2 *beams;            // [BT][D][KP] complex beam spectra   (delay-and-sum fan)
+  int KP;                   // spectrum pitch of `beams`
+  float out_scale;          // 1 / M
 };
 
-template <int NKC>   // K chunks per bin = 2M / 32 = M / 16
+// FAN = true is the delay-and-sum fan of Beamformer::processFrame (Beamformer.cpp:51-71) steered to every direction of the tile: the
+// same contraction on the raw spectra, and the epilogue writes Y / M for every bin instead of accumulating |Y|^2 over bins.
+template <int NKC, bool FAN>   // K chunks per bin = 2M / 32 = M / 16
 __global__ void __launch_bounds__(TC_THREADS, 1) srp_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                                                                 const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -304,6 +315,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) srp_tc_kernel(const __grid_cons
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int ks = item / (p.n_tt * p.n_dt), tt = (item / p.n_dt) % p.n_tt, dt = item % p.n_dt;
       const int k_begin = ks * p.bins_per_range, k_end = min(p.K, k_begin + p.bins_per_range);
+      const long long t = (long long)tt * TC_BM + quarter * 32 + lane;
+      if constexpr (FAN) {
+        const int d0 = dt * TC_BD + half * HD;
+        float2 *row = p.beams + (t * p.D + d0) * p.KP;   // direction d0 of frame t; only dereferenced when t < BT and d < D
+        for (int k = k_begin; k < k_end; ++k) {
+          mbar_wait_bounded(&tmem_full[acc], acc_phase);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + half * HD);
+#pragma unroll
+          for (int j = 0; j < HD / 16; ++j) {
+            float vr[16], vi[16];
+            tmem_ld16(taddr + j * 16, vr);
+            tmem_ld16(taddr + TC_BD + j * 16, vi);
+            if (t < p.BT) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int dd = j * 16 + i;
+                if (d0 + dd < p.D) {
+                  float2 *o = row + (size_t)dd * p.KP + k;
+                  *o = make_float2(vr[i] * p.out_scale, vi[i] * p.out_scale);
+                  if (k == p.K - 1) o[1] = make_float2(0.f, 0.f);   // the pad bin of the row
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[acc]);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        continue;
+      }
       float sum[HD];
 #pragma unroll
       for (int i = 0; i < HD; ++i) sum[i] = 0.f;
@@ -323,7 +365,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) srp_tc_kernel(const __grid_cons
         mbar_arrive(&tmem_empty[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      const long long t = (long long)tt * TC_BM + quarter * 32 + lane;
       if (t < p.BT) {
         const int d0 = dt * TC_BD + half * HD;
         float *dst = p.partial + (((long long)ks * p.BT + t) * p.D) + d0;
@@ -380,8 +421,8 @@ static int encode_map(CUtensorMap *map, const float *base, long long BTpad, int 
   return 0;
 }
 
-template <int NKC> static void launch_tc(int grid, cudaStream_t st, const CUtensorMap &hi, const CUtensorMap &lo, const TcParams &p) {
-  auto kern = srp_tc_kernel<NKC>;
+template <int NKC, bool FAN = false> static void launch_tc(int grid, cudaStream_t st, const CUtensorMap &hi, const CUtensorMap &lo, const TcParams &p) {
+  auto kern = srp_tc_kernel<NKC, FAN>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
   kern<<<grid, TC_THREADS, TC_SMEM, st>>>(hi, lo, p);
 }
@@ -432,7 +473,7 @@ int k_srp_tensor_ws(const float2 *spec, int B, int T, int M, int N, const uint64
   float *Uhi = reinterpret_cast<float *>(w), *Ulo = reinterpret_cast<float *>(w + u_bytes), *partial = reinterpret_cast<float *>(w + 2 * u_bytes),
         *nzsum = reinterpret_cast<float *>(w + 2 * u_bytes + part_bytes);
   p.partial = partial;
-  srp_prepare_kernel<<<(unsigned)BTpad, 256, 0, st>>>(spec, BT, BTpad, M, N, Uhi, Ulo, nzsum);
+  srp_prepare_kernel<true><<<(unsigned)BTpad, 256, 0, st>>>(spec, BT, BTpad, M, N, Uhi, Ulo, nzsum);
   MCAG_CHECK_LAUNCH();
   CUtensorMap map_hi, map_lo;
   OK_RC(encode_map(&map_hi, Uhi, BTpad, M, K));
@@ -453,6 +494,58 @@ int k_srp_tensor_ws(const float2 *spec, int B, int T, int M, int N, const uint64
   srp_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, p.n_ks, BT, D, nzsum, srp);
   MCAG_CHECK_LAUNCH();
   return 0;
+}
+
+// ---- delay-and-sum fan on the same kernel -----------------------------------------------------------------------------------
+// scratch: [X_hi | X_lo], each 1 KB aligned
+size_t k_ds_fan_tensor_workspace_bytes(long long BT, int M, int N) {
+  if (!k_srp_tensor_supported(M) || BT <= 0) return 0;
+  const long long BTpad = (BT + TC_BM - 1) / TC_BM * TC_BM;
+  auto al = [](size_t n) { return (n + 1023) & ~(size_t)1023; };
+  return 2 * al((size_t)(N / 2 + 1) * BTpad * 2 * M * 4);
+}
+int k_ds_fan_tensor_ws(const float2 *spec, int B, int T, int M, int N, const uint64_t *steer_fx, int D, float2 *out, void *workspace, size_t ws_bytes,
+                       cudaStream_t st) {
+  if (B <= 0 || T <= 0) return 0;
+  if (!k_srp_tensor_supported(M)) return k_ds_fan(spec, B, T, M, N, steer_fx, D, out, st);
+  const long long BT = (long long)B * T;
+  TcParams p; long long BTpad;
+  tc_plan(BT, M, N, D, p, BTpad);
+  p.mic_fx = steer_fx; p.partial = nullptr; p.beams = out; p.KP = spec_pitch(N); p.out_scale = 1.0f / (float)M;
+  const int K = p.K;
+  auto al = [](size_t n) { return (n + 1023) & ~(size_t)1023; };
+  const size_t u_bytes = al((size_t)K * BTpad * 2 * M * sizeof(float));
+  if (2 * u_bytes > ws_bytes) return mcag_set_error(4, "ds_fan_tensor: workspace too small");
+  unsigned char *w = static_cast<unsigned char *>(workspace);
+  float *Xhi = reinterpret_cast<float *>(w), *Xlo = reinterpret_cast<float *>(w + u_bytes);
+  srp_prepare_kernel<false><<<(unsigned)BTpad, 256, 0, st>>>(spec, BT, BTpad, M, N, Xhi, Xlo, nullptr);
+  MCAG_CHECK_LAUNCH();
+  CUtensorMap map_hi, map_lo;
+  OK_RC(encode_map(&map_hi, Xhi, BTpad, M, K));
+  OK_RC(encode_map(&map_lo, Xlo, BTpad, M, K));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long items = (long long)p.n_tt * p.n_dt * p.n_ks;
+  const int grid = (int)(items < sms ? items : sms);
+  switch (M / 16) {
+    case 1: launch_tc<1, true>(grid, st, map_hi, map_lo, p); break;
+    case 2: launch_tc<2, true>(grid, st, map_hi, map_lo, p); break;
+    case 3: launch_tc<3, true>(grid, st, map_hi, map_lo, p); break;
+    default: launch_tc<4, true>(grid, st, map_hi, map_lo, p); break;
+  }
+  MCAG_CHECK_LAUNCH();
+  return 0;
+}
+int k_ds_fan_tensor(const float2 *spec, int B, int T, int M, int N, const uint64_t *steer_fx, int D, float2 *out, cudaStream_t st) {
+  if (B <= 0 || T <= 0) return 0;
+  if (!k_srp_tensor_supported(M)) return k_ds_fan(spec, B, T, M, N, steer_fx, D, out, st);
+  const size_t bytes = k_ds_fan_tensor_workspace_bytes((long long)B * T, M, N);
+  void *ws = nullptr;
+  if (cudaMallocAsync(&ws, bytes, st) != cudaSuccess) return mcag_set_cuda_error(cudaGetLastError());
+  const int rc = k_ds_fan_tensor_ws(spec, B, T, M, N, steer_fx, D, out, ws, bytes, st);
+  cudaFreeAsync(ws, st);
+  return rc;
 }
 
 // kernel-level entry without a caller-owned workspace: stream-ordered scratch from the device's memory pool
@@ -476,6 +569,9 @@ int k_srp_tensor(const float2 *spec, int B, int T, int M, int N, const uint64_t 
 
 }  // namespace mcag
 
+extern "C" int mcag_k_ds_fan_tensor(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_steer_fx, int D, void *d_out, void *stream) {
+  return mcag::k_ds_fan_tensor((const float2 *)d_spec, B, T, M, N, d_steer_fx, D, (float2 *)d_out, (cudaStream_t)stream);
+}
 extern "C" int mcag_k_srp_tensor(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_mic_fx, int D, float *d_srp, void *stream) {
   return mcag::k_srp_tensor((const float2 *)d_spec, B, T, M, N, d_mic_fx, D, d_srp, (cudaStream_t)stream);
 }

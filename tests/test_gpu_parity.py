@@ -387,3 +387,32 @@ def test_srp_tensor_kernel_vs_cuda_core_kernel(mb, M, BT, D, N):
     assert np.isfinite(a).all()
     scale = np.max(np.abs(b), axis=1, keepdims=True)
     assert np.max(np.abs(a - b) / (ATOL + RTOL * scale)) <= 1.0, np.max(np.abs(a - b) / scale)
+
+
+@pytest.mark.parametrize("M,BT,D,N", [(32, 200, 181, 512), (16, 130, 70, 256), (64, 5, 300, 1024), (48, 128, 128, 2048)])
+def test_ds_fan_tensor_kernel_vs_cuda_core_kernel(mb, M, BT, D, N):
+    """K4 fan on tcgen05 (srp_tc_kernel<NKC, FAN>: 3xTF32 contraction of the raw spectra, beams written per bin) against the CUDA-core
+    register-tile kernel on the same random spectra: partial frame / direction tiles, every supported microphone count, pad bin zero."""
+    import ctypes as C
+    import torch
+    from mcarray_b200 import capi
+    lib = capi.lib()
+    g = torch.Generator(device="cuda").manual_seed(M * 1000 + BT)
+    KP = N // 2 + 2
+    spec = torch.randn(BT, M, KP, 2, device="cuda", generator=g) * 1000
+    spec[:, :, N // 2 + 1:] = 0
+    spec[:, :, 0, 1] = 0; spec[:, :, N // 2, 1] = 0
+    rng = np.random.default_rng(D)
+    turns = np.ascontiguousarray(rng.uniform(-40, 40, size=(D, M)) / N)
+    fx = torch.empty(D * M, dtype=torch.int64, device="cuda")
+    capi.check(lib.mcag_k_phase_fx(capi.dp(turns), C.c_longlong(D * M), capi.vp(fx), None))
+    out_c = torch.full((BT, D, KP, 2), 7.0, device="cuda"); out_t = torch.full((BT, D, KP, 2), 7.0, device="cuda")
+    torch.cuda.synchronize()
+    capi.check(lib.mcag_k_ds_fan(capi.vp(spec), 1, BT, M, N, capi.vp(fx), D, capi.vp(out_c), None))
+    capi.check(lib.mcag_k_ds_fan_tensor(capi.vp(spec), 1, BT, M, N, capi.vp(fx), D, capi.vp(out_t), None))
+    torch.cuda.synchronize()
+    a, b = out_t.cpu().numpy(), out_c.cpu().numpy()
+    assert np.isfinite(a).all()
+    assert np.all(a[:, :, N // 2 + 1:] == 0) and np.all(b[:, :, N // 2 + 1:] == 0)         # pad bin
+    scale = np.max(np.abs(b), axis=(1, 2, 3), keepdims=True)
+    assert np.max(np.abs(a - b) / (ATOL + RTOL * scale)) <= 1.0, np.max(np.abs(a - b) / scale)
