@@ -94,21 +94,27 @@ __global__ void __launch_bounds__(256) gate_kernel(const float *__restrict__ cha
   }
 }
 
-// hold the last active selection on gated-off frames (_currentDOA / _prob persist, BSAL.cpp:87-95)
-__global__ void carry_cells_kernel(const int32_t *__restrict__ raw_idx, const float *__restrict__ raw_prob, const unsigned char *__restrict__ active,
-                                   int B, int T, int S, int32_t *__restrict__ cell_state, float *__restrict__ prob_state,
-                                   int32_t *__restrict__ cells, float *__restrict__ prob) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * S) return;
-  const int b = i / S, s = i - b * S;
-  int32_t c = cell_state[i];
-  float p = prob_state[i];
-  for (int t = 0; t < T; ++t) {
+// hold the last active selection on gated-off frames (_currentDOA / _prob persist, BSAL.cpp:87-95).  One CTA per stream: every frame
+// looks back to the nearest active frame of the call (usually itself), or to the carried state when there is none.
+__global__ void __launch_bounds__(128) carry_cells_kernel(const int32_t *__restrict__ raw_idx, const float *__restrict__ raw_prob,
+                                                           const unsigned char *__restrict__ active, int B, int T, int S,
+                                                           int32_t *__restrict__ cell_state, float *__restrict__ prob_state,
+                                                           int32_t *__restrict__ cells, float *__restrict__ prob) {
+  const int b = blockIdx.x;
+  const unsigned char *act = active + (long long)b * T;
+  for (int i = threadIdx.x; i < T * S; i += blockDim.x) {
+    const int t = i / S, s = i - t * S;
+    int u = t;
+    while (u >= 0 && !act[u]) --u;
     const long long o = ((long long)b * T + t) * S + s;
-    if (active[(long long)b * T + t]) { c = raw_idx[o]; p = raw_prob[o]; }
-    cells[o] = c; prob[o] = p;
+    if (u >= 0) { const long long src = ((long long)b * T + u) * S + s; cells[o] = raw_idx[src]; prob[o] = raw_prob[src]; }
+    else { cells[o] = cell_state[b * S + s]; prob[o] = prob_state[b * S + s]; }
   }
-  cell_state[i] = c; prob_state[i] = p;
+  __syncthreads();   // every read of the carried state is done
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const long long o = ((long long)b * T + (T - 1)) * S + s;
+    cell_state[b * S + s] = cells[o]; prob_state[b * S + s] = prob[o];
+  }
 }
 
 int k_frame_power_raw(const float2 *spec, long long rows, int N, float *raw, cudaStream_t st);   // below
@@ -571,12 +577,11 @@ static int run_frames(mcag_proc p, const float *x_all, long long pitch, int T, i
     p->launches++;
   } else {
     PROF(MCAG_PROF_STFT);
-    OK(k_stft(x, pitch, B * M, M, T, N, hop, win, tw, spec, chan_pow, st));
-    p->launches += (N == 256) ? 2 : 1;
+    OK(k_stft(x, pitch, B * M, M, T, N, hop, win, tw, spec, chan_pow, chan_raw, st));   // chan_raw: only with floor_ccs_power (FreqGCC)
+    p->launches += (N == 256) ? (chan_raw ? 3 : 2) : 1;
   }
   if (kind != MCAG_KIND_MULTIBAND) {
     PROF(MCAG_PROF_GATE);
-    if (p->cfg.floor_ccs_power) { OK(k_frame_power_raw(spec, BT * M, N, chan_raw, st)); p->launches++; }
     const int needed = (int)(p->cfg.floor_seconds * (float)p->cfg.sample_rate);
     gate_kernel<<<B, 256, 0, st>>>(chan_pow, chan_raw, B, T, M, N, p->cfg.use_power_floor, p->cfg.floor_ccs_power, p->cfg.noise_margin_db, needed,
                                    p->gate.as<GateState>() + o, p->power_db.as<float>() + o * T, active);
@@ -591,7 +596,7 @@ static int run_frames(mcag_proc p, const float *x_all, long long pitch, int T, i
     int32_t *raw_idx = p->raw_idx.as<int32_t>() + o * T * S;
     float *raw_prob = p->raw_prob.as<float>() + o * T * S;
     OK(k_select_doa(energy, BT, D, P, S, raw_idx, raw_prob, st));
-    carry_cells_kernel<<<(B * S + 127) / 128, 128, 0, st>>>(raw_idx, raw_prob, active, B, T, S, p->cell_state.as<int32_t>() + o * S,
+    carry_cells_kernel<<<B, 128, 0, st>>>(raw_idx, raw_prob, active, B, T, S, p->cell_state.as<int32_t>() + o * S,
                                                             p->prob_state.as<float>() + o * S, p->cells.as<int32_t>() + o * T * S,
                                                             p->prob.as<float>() + o * T * S);
     MCAG_CHECK_LAUNCH();
@@ -1010,7 +1015,7 @@ int mcag_k_phase_fx(const double *h_turns, long long n, uint64_t *d_fx, void *st
 }
 int mcag_k_stft(const float *d_x, long long row_pitch, int rows, int M, int T, int N, int hop, const float *d_win, const void *d_tw, void *d_spec,
                 float *d_chan_pow, void *stream) {
-  return k_stft(d_x, row_pitch, rows, M, T, N, hop, d_win, (const float2 *)d_tw, (float2 *)d_spec, d_chan_pow, (cudaStream_t)stream);
+  return k_stft(d_x, row_pitch, rows, M, T, N, hop, d_win, (const float2 *)d_tw, (float2 *)d_spec, d_chan_pow, nullptr, (cudaStream_t)stream);
 }
 int mcag_k_istft(const void *d_spec, int B, int T, int C_in, int C_out, int N, int hop, const float *d_win, const void *d_tw, const float *d_tail_in,
                  float *d_tail_out, float *d_out, long long out_pitch, void *stream) {

@@ -18,17 +18,30 @@ __global__ void pair_sum_kernel(const float *__restrict__ corr, long long BT, in
   esum[i] = acc;
 }
 
-// E_t = a * E_{t-1} + esum_t on active frames, E_t = E_{t-1} otherwise; one thread per (stream, direction).
-__global__ void energy_scan_kernel(const float *__restrict__ esum, int B, int T, int D, float a, const unsigned char *__restrict__ active,
-                                   float *__restrict__ state, float *__restrict__ energy) {
+// E_t = a * E_{t-1} + esum_t on active frames, E_t = E_{t-1} otherwise; one thread per (stream, direction).  The inputs of 8 frames are
+// fetched before the recurrence touches them (esum and energy may be the same buffer, so the compiler cannot hoist the loads itself):
+// the scan is a chain of dependent FMAs, not a chain of dependent memory round trips.
+__global__ void energy_scan_kernel(const float *esum, int B, int T, int D, float a, const unsigned char *__restrict__ active,
+                                   float *__restrict__ state, float *energy) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * D) return;
   const int b = i / D, d = i - b * D;
   float e = state[i];
-  for (int t = 0; t < T; ++t) {
-    const long long o = ((long long)b * T + t) * D + d;
-    if (!active || active[(long long)b * T + t]) e = fmaf(a, e, esum[o]);
-    energy[o] = e;
+  constexpr int CH = 8;
+  for (int t0 = 0; t0 < T; t0 += CH) {
+    float in[CH]; bool on[CH];
+#pragma unroll
+    for (int u = 0; u < CH; ++u) {
+      const int t = t0 + u;
+      in[u] = (t < T) ? esum[((long long)b * T + t) * D + d] : 0.f;
+      on[u] = (t < T) && (!active || active[(long long)b * T + t]);
+    }
+#pragma unroll
+    for (int u = 0; u < CH; ++u) {
+      const int t = t0 + u;
+      if (on[u]) e = fmaf(a, e, in[u]);
+      if (t < T) energy[((long long)b * T + t) * D + d] = e;
+    }
   }
   state[i] = e;
 }

@@ -7,7 +7,7 @@ namespace mcag {
 
 // stft.cu
 int k_stft(const float *x, long long row_pitch, int rows, int M, int T, int N, int hop, const float *win, const float2 *tw, float2 *spec,
-           float *chan_pow, cudaStream_t st);
+           float *chan_pow, float *chan_raw /* plain sum of |X|^2 per (frame, channel), may be NULL */, cudaStream_t st);
 int k_istft(const float2 *spec, int B, int T, int C_in, int C_out, int N, int hop, const float *win, const float2 *tw, const float *tail_in,
             float *tail_out, float *out, long long out_pitch, int out_rows /* rows per stream in `out`, >= C_out */, cudaStream_t st);
 int k_frame_power(const float2 *spec, long long rows, int N, float *pow, cudaStream_t st);

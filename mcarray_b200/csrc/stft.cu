@@ -7,6 +7,8 @@
 
 namespace mcag {
 
+int k_frame_power_raw(const float2 *spec, long long rows, int N, float *raw, cudaStream_t st);   // capi.cu
+
 // ---------------------------------------------------------------------------------------------------
 // K1: persistent CTAs walk work items = F consecutive frames of one (stream, channel) row.  The window and the FFT
 // tables are loaded once per CTA; the (F-1)*hop + N samples the frames of an item share are staged into shared memory
@@ -17,8 +19,8 @@ namespace mcag {
 template <int N, int F, int G>
 __global__ void __launch_bounds__(G *(N / 16)) stft_kernel(const float *__restrict__ x, long long row_pitch, int M, int T, int hop,
                                                             const float *__restrict__ win, const float2 *__restrict__ tw_g,
-                                                            float2 *__restrict__ spec, float *__restrict__ chan_pow, int tiles_per_row,
-                                                            long long n_items) {
+                                                            float2 *__restrict__ spec, float *__restrict__ chan_pow, float *__restrict__ chan_raw,
+                                                            int tiles_per_row, long long n_items) {
   constexpr int NC = N / 2, TPF = NC / 8, KP = spec_pitch(N), NT = G * TPF, XLEN = (F - 1) * N + N;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char *smem = fft_align_smem(smem_raw, 8 * NC);
@@ -27,7 +29,7 @@ __global__ void __launch_bounds__(G *(N / 16)) stft_kernel(const float *__restri
   float *s_w = s_xb + 2 * XLEN;                                       // N
   float2 *s_tw = reinterpret_cast<float2 *>(s_w + N);                 // fft_table_len(N): tw[NC] then twp
   float2 *s_twp = s_tw + NC;                                          // per-thread inter-pass twiddles
-  float *s_red = reinterpret_cast<float *>(s_tw + fft_table_len(N));  // G * (TPF/32 or 1)
+  float *s_red = reinterpret_cast<float *>(s_tw + fft_table_len(N));  // 2 x G * (TPF/32 or 1): Parseval power, plain sum of |X|^2
   __shared__ __align__(8) uint64_t s_bar[2];
 
   const int tid = threadIdx.x;
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(G *(N / 16)) stft_kernel(const float *__restri
         fft_run<NC, false>(v, buf, s_twp, j, g);
         // real post-processing: X[k] = E + W^k O, X[NC-k] = conj(E - W^k O); k = j + i*TPF (i < 4), and k = NC/2 for j = 0
         float2 *out = spec + (((long long)b * T + (t0 + f)) * M + m) * KP;
-        float pw = 0.f;
+        float pw = 0.f, pr = 0.f;
         auto post = [&](int k) {
           float2 zk = fft_buf_get(buf, k), zn = fft_buf_get(buf, (NC - k) & (NC - 1));
           float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
@@ -97,8 +99,9 @@ __global__ void __launch_bounds__(G *(N / 16)) stft_kernel(const float *__restri
           out[k] = xk;
           out[NC - k] = xn;
           const float wk = (k == 0) ? 1.f : 2.f;
-          pw += wk * (xk.x * xk.x + xk.y * xk.y);
-          if (k != NC - k) pw += wk * (xn.x * xn.x + xn.y * xn.y);
+          const float mk = xk.x * xk.x + xk.y * xk.y, mn = (k != NC - k) ? xn.x * xn.x + xn.y * xn.y : 0.f;
+          pw += wk * (mk + mn);
+          pr += mk + mn;   // plain sum over the K bins: mean square of the CCS buffer (BinauralLocalisation.cpp:390-391)
         };
 #pragma unroll
         for (int i = 0; i < 4; ++i) post(j + i * TPF);
@@ -107,13 +110,15 @@ __global__ void __launch_bounds__(G *(N / 16)) stft_kernel(const float *__restri
         constexpr int WPF = (TPF + 31) / 32;
         if constexpr (TPF >= 32) {   // N = 256 packs two transforms per warp: its power comes from frame_power_kernel
           pw = warp_sum(pw);
+          if (chan_raw) pr = warp_sum(pr);
           if (chan_pow) {
-            if ((tid & 31) == 0) s_red[g * WPF + (j >> 5)] = pw;
+            if ((tid & 31) == 0) { s_red[g * WPF + (j >> 5)] = pw; s_red[(G + g) * WPF + (j >> 5)] = pr; }
             group_sync<TPF>(g);
             if (j == 0) {
-              float sacc = 0.f;
-              for (int i = 0; i < WPF; ++i) sacc += s_red[g * WPF + i];
+              float sacc = 0.f, racc = 0.f;
+              for (int i = 0; i < WPF; ++i) { sacc += s_red[g * WPF + i]; racc += s_red[(G + g) * WPF + i]; }
               chan_pow[((long long)b * T + (t0 + f)) * M + m] = sacc / ((float)N * (float)N);
+              if (chan_raw) chan_raw[((long long)b * T + (t0 + f)) * M + m] = racc;
             }
           }
         }
@@ -230,12 +235,12 @@ __global__ void __launch_bounds__(G *(N / 16)) istft_kernel(const float2 *__rest
 }
 
 template <int N> static int launch_stft(const float *x, long long row_pitch, int rows, int M, int T, int hop, const float *win,
-                                        const float2 *tw, float2 *spec, float *chan_pow, cudaStream_t st) {
+                                        const float2 *tw, float2 *spec, float *chan_pow, float *chan_raw, cudaStream_t st) {
   constexpr int NC = N / 2, TPF = NC / 8;
   constexpr int G = (TPF >= 128) ? 2 : (256 / TPF);
   constexpr int F = (N >= 2048) ? 4 : (G > 8 ? G : 8);
   size_t smem = sizeof(float) * 2 * ((F - 1) * N + N) + sizeof(float) * N + sizeof(float2) * fft_table_len(N) + sizeof(float2) * G * fft_buf_len(NC) +
-                sizeof(float) * G * 4 + 8 * NC /* buffer alignment slack */;
+                sizeof(float) * G * 8 + 8 * NC /* buffer alignment slack */;
   auto kern = stft_kernel<N, F, G>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   static int sm_count = 0, dev_cached = -1;
@@ -248,12 +253,14 @@ template <int N> static int launch_stft(const float *x, long long row_pitch, int
   const int tiles_per_row = (T + F - 1) / F;
   const long long n_items = (long long)tiles_per_row * rows, cap = (long long)sm_count * per_sm;
   float *pow_in_kernel = (TPF >= 32) ? chan_pow : nullptr;
-  kern<<<(unsigned)(n_items < cap ? n_items : cap), G * TPF, smem, st>>>(x, row_pitch, M, T, hop, win, tw, spec, pow_in_kernel, tiles_per_row, n_items);
+  kern<<<(unsigned)(n_items < cap ? n_items : cap), G * TPF, smem, st>>>(x, row_pitch, M, T, hop, win, tw, spec, pow_in_kernel,
+                                                                         pow_in_kernel ? chan_raw : nullptr, tiles_per_row, n_items);
   MCAG_CHECK_LAUNCH();
   if (chan_pow && TPF < 32) {
     long long nrows = (long long)(rows / M) * T * M;
     frame_power_kernel<<<(unsigned)((nrows + 7) / 8), 256, 0, st>>>(spec, nrows, N, chan_pow);
     MCAG_CHECK_LAUNCH();
+    if (chan_raw) return k_frame_power_raw(spec, nrows, N, chan_raw, st);
   }
   return 0;
 }
@@ -281,14 +288,14 @@ template <int N> static int launch_istft(const float2 *spec, int B, int T, int C
 }
 
 int k_stft(const float *x, long long row_pitch, int rows, int M, int T, int N, int hop, const float *win, const float2 *tw, float2 *spec,
-           float *chan_pow, cudaStream_t st) {
+           float *chan_pow, float *chan_raw, cudaStream_t st) {
   if (T <= 0) return 0;
   if (hop <= 0 || hop > N || (hop & 1) || (N % hop)) return mcag_set_error(1, "stft: hop must be even and divide N");
   switch (N) {
-    case 256: return launch_stft<256>(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, st);
-    case 512: return launch_stft<512>(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, st);
-    case 1024: return launch_stft<1024>(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, st);
-    case 2048: return launch_stft<2048>(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, st);
+    case 256: return launch_stft<256>(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, chan_raw, st);
+    case 512: return launch_stft<512>(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, chan_raw, st);
+    case 1024: return launch_stft<1024>(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, chan_raw, st);
+    case 2048: return launch_stft<2048>(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, chan_raw, st);
   }
   return mcag_set_error(1, "stft: frame size must be 256, 512, 1024 or 2048");
 }
