@@ -61,6 +61,15 @@ __device__ __forceinline__ void warp_argmax(float &v, int &i) {
   }
 }
 
+// order-preserving map float -> uint32 (a < b  <=>  key(a) < key(b) for non-NaN a, b with -0 folded into +0 by the caller)
+__device__ __forceinline__ unsigned float_order_key(float v) {
+  const unsigned u = __float_as_uint(v);
+  return u ^ ((unsigned)((int)u >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float float_from_order_key(unsigned k) {
+  return __uint_as_float(k ^ ((k & 0x80000000u) ? 0x80000000u : 0xffffffffu));
+}
+
 // ---- mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) ------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {

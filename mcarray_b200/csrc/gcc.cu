@@ -37,19 +37,19 @@ __device__ __forceinline__ void pair_table(unsigned char *s_pair, int M, int P, 
   }
 }
 
-// E/O twiddles conj(W_N^k) of the packed inverse real transform for the 8 bins k = j + r*TPF this thread builds: the same for
-// every pair and frame, so they live in registers
-template <int N> __device__ __forceinline__ void load_eo_twiddles(const float2 *s_tw, int j, float2 (&wk)[8]) {
+// E/O twiddles conj(W_N^k) of the packed inverse real transform for the 4 bins k = j + r*TPF (r < 4) this thread builds: the
+// same for every pair and frame, so they live in registers
+template <int N> __device__ __forceinline__ void load_eo_twiddles(const float2 *s_tw, int j, float2 (&wk)[4]) {
   constexpr int NC = N / 2, TPF = NC / 8;
 #pragma unroll
-  for (int r = 0; r < 8; ++r) wk[r] = tw_lookup<true>(s_tw, j + r * TPF, NC);
+  for (int r = 0; r < 4; ++r) wk[r] = tw_lookup<true>(s_tw, j + r * TPF, NC);
 }
 
 // all P pairs of the frame whose whitened spectra are in s_U; every thread of the CTA calls it (uniform trip count).
 // The lag window only needs the lowest and highest NC/R_last outputs of the inverse transform, so its last pass is
 // output-pruned (fft_inv_last_pruned): nothing is stored, the window values go from registers into the arg-max.
 template <int N, int G>
-__device__ __forceinline__ void tdoa_pairs(const float2 *s_U, const float2 (&wk)[8], const float2 *s_twp, fft_buf_t buf, const unsigned char *s_pair,
+__device__ __forceinline__ void tdoa_pairs(const float2 *s_U, const float2 (&wk)[4], const float2 *s_twp, fft_buf_t buf, const unsigned char *s_pair,
                                            float *s_bv, int *s_bi, int P, int max_lag, int g, int j, float *__restrict__ curves_ft,
                                            int32_t *__restrict__ lags_ft, float *__restrict__ peaks_ft) {
   constexpr int NC = N / 2, TPF = NC / 8, KP = spec_pitch(N);
@@ -64,17 +64,31 @@ __device__ __forceinline__ void tdoa_pairs(const float2 *s_U, const float2 (&wk)
     const bool live = p < P;
     const int pc = live ? p : P - 1;
     const float2 *Ui = s_U + (size_t)s_pair[2 * pc] * KP, *Uj = s_U + (size_t)s_pair[2 * pc + 1] * KP;
+    // Mirrored build of the transform input: the bins k and NC-k need the same two cross-spectrum values, Z[k] = E + iO and
+    // Z[NC-k] = conj(E) + i conj(O), so a thread forms each bin pair ONCE (k = j + r*TPF, r < 4: half the loads and half the
+    // arithmetic of building its 8 first-pass points itself).  Z[k] is its own first-pass point r; Z[NC-k] is point 7-r of the
+    // partner thread TPF-j, handed over through the partner's private pass-0 region of the transform buffer (slots 8p..8p+7,
+    // which only p itself overwrites afterwards).  Thread TPF/2 is its own partner; thread 0 pairs (r*TPF, (8-r)*TPF) inside
+    // itself and also forms the self-paired bin NC/2.
     float2 v[8];
+    const int pj = (j == 0) ? 0 : TPF - j;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int k = j + r * (NC / 8);
+    for (int r = 0; r < 4; ++r) {
+      const int k = j + r * TPF;
       float2 gk = cmulc(Ui[k], Uj[k]), gn = cmulc(Ui[NC - k], Uj[NC - k]);
       if (k == 0) { gk.y = 0.f; gn.y = 0.f; }
       float2 e = make_float2(0.5f * (gk.x + gn.x), 0.5f * (gk.y - gn.y));
       float2 d = make_float2(0.5f * (gk.x - gn.x), 0.5f * (gk.y + gn.y));
       float2 o = cmul(d, wk[r]);
       v[r] = make_float2(e.x - o.y, e.y + o.x);
+      const float2 zn = make_float2(e.x + o.y, o.x - e.y);
+      if (j != 0) sts64(buf ^ (8u * (uint32_t)fft_pad(8 * pj + 7 - r)), zn);
+      else if (r != 0) sts64(buf ^ (8u * (uint32_t)fft_pad(8 - r)), zn);
     }
+    if (j == 0) sts64(buf ^ (8u * (uint32_t)fft_pad(4)), cmulc(Uj[NC / 2], Ui[NC / 2]));   // Z[NC/2] = conj(G[NC/2])
+    group_sync<TPF>(g);
+#pragma unroll
+    for (int r = 4; r < 8; ++r) v[r] = lds64(buf ^ (8u * (uint32_t)fft_pad(8 * j + r)));
     const float g0 = Ui[0].x * Uj[0].x, gny = Ui[NC].x * Uj[NC].x;   // both spectra are real at DC / Nyquist
     const float b_even = 0.5f * (g0 + gny), b_odd = 0.5f * (g0 - gny);
     float *cdst = (curves_ft && live) ? curves_ft + (size_t)p * L : nullptr;
@@ -119,17 +133,22 @@ __device__ __forceinline__ void tdoa_pairs(const float2 *s_U, const float2 (&wk)
     }
     // first-maximum argmax across the group
     if constexpr (TPF >= 32) {
-      warp_argmax(best, besti);
+      // two REDUX instructions per warp instead of a 5-step shuffle tree: maximum of the order-preserving integer image of
+      // the value (x + 0 folds -0 into +0 so that equal floats have equal keys), then the lowest window index that attains it
       constexpr int WPF = TPF / 32;
-      if ((threadIdx.x & 31) == 0) { s_bv[g * WPF + (j >> 5)] = best; s_bi[g * WPF + (j >> 5)] = besti; }
+      const unsigned key = float_order_key(best + 0.f);
+      const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
+      const unsigned imin = __reduce_min_sync(0xffffffffu, key == kmax ? (unsigned)besti : 0x7fffffffu);
+      unsigned *s_bk = reinterpret_cast<unsigned *>(s_bv) + (it & 1) * (G * WPF);   // double-buffered by round: one sync per round
+      int *s_bx = s_bi + (it & 1) * (G * WPF);
+      if ((threadIdx.x & 31) == 0) { s_bk[g * WPF + (j >> 5)] = kmax; s_bx[g * WPF + (j >> 5)] = (int)imin; }
       group_sync<TPF>(g);   // also: every thread of the group is done reading buf
       if (j == 0 && live) {
-        float bv = s_bv[g * WPF]; int bi = s_bi[g * WPF];
-        for (int w = 1; w < WPF; ++w) { float ov = s_bv[g * WPF + w]; int oi = s_bi[g * WPF + w]; if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; } }
+        unsigned bk = s_bk[g * WPF]; int bi = s_bx[g * WPF];
+        for (int w = 1; w < WPF; ++w) { unsigned ok = s_bk[g * WPF + w]; int oi = s_bx[g * WPF + w]; if (ok > bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; } }
         lags_ft[p] = bi - max_lag;
-        if (peaks_ft) peaks_ft[p] = bv;
+        if (peaks_ft) peaks_ft[p] = float_from_order_key(bk);
       }
-      group_sync<TPF>(g);   // s_bv / s_bi are rewritten by the next round
     } else {
       const unsigned gmask = ((1u << (TPF & 31)) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(TPF - 1));
 #pragma unroll
@@ -159,9 +178,9 @@ __global__ void __launch_bounds__(G *(N / 16)) tdoa_kernel(const float2 *__restr
   float2 *s_U = s_buf + G * fft_buf_len(NC);                          // M * KP
   float2 *s_tw = s_U + (size_t)M * KP;                                // fft_table_len(N): tw[NC] then twp
   float2 *s_twp = s_tw + NC;
-  float *s_bv = reinterpret_cast<float *>(s_tw + fft_table_len(N));   // G * WPF
-  int *s_bi = reinterpret_cast<int *>(s_bv + G * WPF);                // G * WPF
-  unsigned char *s_pair = reinterpret_cast<unsigned char *>(s_bi + G * WPF);   // 2 * P
+  float *s_bv = reinterpret_cast<float *>(s_tw + fft_table_len(N));   // 2 * G * WPF (double-buffered by pair round)
+  int *s_bi = reinterpret_cast<int *>(s_bv + 2 * G * WPF);            // 2 * G * WPF
+  unsigned char *s_pair = reinterpret_cast<unsigned char *>(s_bi + 2 * G * WPF);   // 2 * P
 
   const int tid = threadIdx.x, t = blockIdx.x, b = blockIdx.y;
   const float2 *src = spec + ((long long)b * T + t) * M * KP;
@@ -174,7 +193,7 @@ __global__ void __launch_bounds__(G *(N / 16)) tdoa_kernel(const float2 *__restr
   __syncthreads();
   const int g = tid / TPF, j = tid % TPF;
   const long long ft = (long long)b * T + t;
-  float2 wk[8];
+  float2 wk[4];
   load_eo_twiddles<N>(s_tw, j, wk);
   tdoa_pairs<N, G>(s_U, wk, s_twp, smem_u32(s_buf + g * fft_buf_len(NC)), s_pair, s_bv, s_bi, P, max_lag, g, j,
                    curves ? curves + ft * P * L : nullptr, lags + ft * P, peaks ? peaks + ft * P : nullptr);
@@ -200,9 +219,9 @@ __global__ void __launch_bounds__(G *(N / 16), 768 / (G * (N / 16))) stft_tdoa_k
   float2 *s_tw = s_U + (size_t)M * KP;                                // fft_table_len(N)
   float2 *s_twp = s_tw + NC;
   float2 *s_w = s_tw + fft_table_len(N);                              // NC (window, pairs of samples)
-  float *s_bv = reinterpret_cast<float *>(s_w + NC);                  // G * WPF
-  int *s_bi = reinterpret_cast<int *>(s_bv + G * WPF);                // G * WPF
-  unsigned char *s_pair = reinterpret_cast<unsigned char *>(s_bi + G * WPF);   // 2 * P
+  float *s_bv = reinterpret_cast<float *>(s_w + NC);                  // 2 * G * WPF (double-buffered by pair round)
+  int *s_bi = reinterpret_cast<int *>(s_bv + 2 * G * WPF);            // 2 * G * WPF
+  unsigned char *s_pair = reinterpret_cast<unsigned char *>(s_bi + 2 * G * WPF);   // 2 * P
 
   const int tid = threadIdx.x;
   fft_load_tables<N>(s_tw, tw_g, tid, NT);
@@ -211,7 +230,7 @@ __global__ void __launch_bounds__(G *(N / 16), 768 / (G * (N / 16))) stft_tdoa_k
   __syncthreads();
   const int g = tid / TPF, j = tid % TPF;
   const fft_buf_t buf = smem_u32(s_buf + g * fft_buf_len(NC));
-  float2 wk[8];
+  float2 wk[4];
   load_eo_twiddles<N>(s_tw, j, wk);
   const bool vec_ok = ((row_pitch & 1) == 0) && ((hop & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
   const long long nframes = (long long)B * T;
@@ -286,7 +305,7 @@ template <int N> static int launch_tdoa(const float2 *spec, int B, int T, int M,
   constexpr int G = (TPF >= 128) ? 2 : (256 / TPF);
   const int P = M * (M - 1) / 2, L = 2 * max_lag + 1;
   size_t smem = sizeof(float2) * ((size_t)M * spec_pitch(N) + fft_table_len(N) + (size_t)G * fft_buf_len(NC)) +
-                8 * G * ((TPF + 31) / 32) + 2 * P + 16 + 8 * NC /* buffer alignment slack */;
+                16 * G * ((TPF + 31) / 32) + 2 * P + 16 + 8 * NC /* buffer alignment slack */;
   if (smem > 220 * 1024) return mcag_set_error(1, "tdoa: M*N too large for the shared-memory staged kernel");
   auto kern = tdoa_kernel<N, G>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -301,7 +320,7 @@ template <int N> static int launch_stft_tdoa(const float *x, long long row_pitch
   constexpr int G = (TPF >= 128) ? 4 : (256 / TPF);
   const int P = M * (M - 1) / 2, L = 2 * max_lag + 1;
   size_t smem = sizeof(float2) * ((size_t)M * spec_pitch(N) + fft_table_len(N) + (size_t)G * fft_buf_len(NC) + NC) +
-                8 * G * ((TPF + 31) / 32) + 2 * P + 16 + 8 * NC /* buffer alignment slack */;
+                16 * G * ((TPF + 31) / 32) + 2 * P + 16 + 8 * NC /* buffer alignment slack */;
   if (smem > 220 * 1024) return mcag_set_error(1, "tdoa: M*N too large for the shared-memory staged kernel");
   auto kern = stft_tdoa_kernel<N, G>;
   static int sm_count = 0, dev_cached = -1;
