@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmcarray_b200.so")
+LIB_PATH = os.environ.get("MCAG_LIB_PATH") or os.path.join(_HERE, "libmcarray_b200.so")   # override: kernel-variant experiments (tools/variants.sh)
 
 KIND_SSL, KIND_SL, KIND_FREQGCC, KIND_MASK, KIND_TDOA, KIND_DSFAN, KIND_SRP, KIND_MULTIBAND = range(8)
 (OUT_SPECTRA, OUT_POWER_DB, OUT_CORR, OUT_ENERGY, OUT_CELL, OUT_PROB, OUT_LAGS, OUT_CURVES, OUT_ACTIVE, OUT_BEAMS,

@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(G *(N / 16), 768 / (G * (N / 16))) stft_tdoa_k
         float2 zk = fft_buf_get(buf, k), zn = fft_buf_get(buf, (NC - k) & (NC - 1));
         float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
         float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));   // -i/2 (zk - conj zn)
-        float2 w = tw_lookup<false>(s_tw, k, NC);
+        float2 w = s_tw[k];   // k <= NC/2: first half of the table, W_N^k itself
         float2 wo = cmul(w, o);
         float2 xk = cadd(e, wo), xn = cconj(csub(e, wo));
         if (k == 0) { xk.y = 0.f; xn.y = 0.f; }
