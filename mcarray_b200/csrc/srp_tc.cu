@@ -105,7 +105,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N = 256, M = 128
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
 
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// hi part of the 3xTF32 split: x rounded to the nearest TF32 (add half a TF32 ulp to the bit pattern, clear the low 13 bits: two
+// ALU operations; cvt.rna.tf32.f32 does the same on the quarter-rate conversion pipe and slowed the producers by 20 %).  With a
+// rounded hi, lo = x - hi is at most half a TF32 ulp and has no preferred sign; with a truncated hi the dropped lo*lo products
+// all carry the sign of the full product and bias |Y|^2 low by ~2^-22 of the sum over bins.
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 
 // ---- pre-pass: whiten, split, transpose to bin-major --------------------------------------------------------------------
 // spec [BT][M][KP] float2  ->  U_hi / U_lo [K][BTpad][2M] fp32 (rows t >= BT stay zero), nzsum[t] = sum_k #(non-zero channels)
@@ -394,6 +398,257 @@ __global__ void srp_reduce_kernel(const float *__restrict__ partial, int n_part,
   srp[i] = 0.5f * (acc - nzsum[i / D]);
 }
 
+// ---- small arrays: M = 16 microphones, D <= 64 directions (the mcbeam-shaped streams of BASELINE config 5) ---------------------
+// With one direction tile the frames operand is read exactly once, so the bin-major hi / lo copy of srp_prepare_kernel (write
+// 2 x 4*2M*K bytes per frame, read them again) costs more than the contraction itself.  This variant has no pre-pass and no TMA:
+//   warps 4-11 (256 producer threads) build BOTH operands of a bin in shared memory: the frames operand straight from the
+//               spectra (thread = (frame row, 8 microphones): 16-byte loads of two bins at a time, one bin pair prefetched,
+//               whiten, 3xTF32 split, swizzled 16-byte stores; the other half of every 32-byte sector is an L1 hit one
+//               iteration later - the kernel keeps 2 stages so that ~96 KB stay L1), and the generated steering operand
+//               (thread = (direction, 4 microphones)); they also count the non-zero (bin, microphone) entries per frame (nz term)
+//   warp 1      MMA issuer: 12 tcgen05.mma.kind::tf32 (M128 N128 K8) per bin into one of two 128-column TMEM accumulators
+//   warps 12-19 epilogue: |Y|^2 accumulated over the bins of the work item (frame tile x bin range), partial map stored
+constexpr int TS_BD = 64;
+constexpr int TS_STAGES = 2;
+constexpr int TS_A_BYTES = TC_BM * TC_KC * 4;          // 16 KB
+constexpr int TS_B_BYTES = 2 * TS_BD * TC_KC * 4;      // 16 KB
+constexpr int TS_STAGE_BYTES = 2 * TS_A_BYTES + 2 * TS_B_BYTES;   // 64 KB
+constexpr int TS_SMEM = TS_STAGES * TS_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t TS_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+struct TsParams {
+  const float2 *spec;    // [BT][16][KP]
+  long long BT;
+  int D, K, KP;
+  int n_tt, n_ks, bins_per_range;   // bins_per_range is even: bin pairs never straddle two ranges
+  const uint64_t *mic_fx;           // [D][16]
+  float *partial;                   // [n_ks][BT][D]
+  float *nzsum;                     // [BT], zeroed before the launch
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) srp_tc_small_kernel(const TsParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TS_STAGES * TS_STAGE_BYTES);
+  uint64_t *full = bars, *empty = bars + TS_STAGES, *tmem_full = bars + 2 * TS_STAGES, *tmem_empty = bars + 2 * TS_STAGES + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TS_STAGES + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < TS_STAGES; ++s) { mbar_init(&full[s], TC_GEN_THREADS); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], TC_EPI_THREADS); }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_items = p.n_tt * p.n_ks;
+
+  if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int ks = item / p.n_tt;
+        const int k_begin = ks * p.bins_per_range, k_end = min(p.K, k_begin + p.bins_per_range);
+        for (int k = k_begin; k < k_end; ++k) {
+          mbar_wait_bounded(&tmem_empty[acc], acc_phase ^ 1);
+          mbar_wait_bounded(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
+          const uint32_t sa = smem_u32(smem + stage * TS_STAGE_BYTES);
+          const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + TS_A_BYTES);
+          const uint64_t b_hi = umma_desc_sw128(sa + 2 * TS_A_BYTES), b_lo = umma_desc_sw128(sa + 2 * TS_A_BYTES + TS_B_BYTES);
+#pragma unroll
+          for (int j = 0; j < TC_KC / 8; ++j) {
+            umma_tf32(d_tmem, a_hi + 2 * j, b_hi + 2 * j, TS_IDESC, j != 0);
+            umma_tf32(d_tmem, a_lo + 2 * j, b_hi + 2 * j, TS_IDESC, 1);
+            umma_tf32(d_tmem, a_hi + 2 * j, b_lo + 2 * j, TS_IDESC, 1);
+          }
+          umma_commit(&empty[stage]);
+          umma_commit(&tmem_full[acc]);
+          if (++stage == TS_STAGES) { stage = 0; phase ^= 1; }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 4 + TC_GEN_THREADS / 32) {
+    // ===== producers: frames operand from the spectra + generated steering operand =====
+    const int g = tid - 128;
+    const int row = g & (TC_BM - 1), half = g >> 7;   // frames operand: frame row of the tile, microphones 8*half .. 8*half+7
+    const int dl = g & (TS_BD - 1), grp = g >> 6;     // steering operand: direction, microphones 4*grp .. 4*grp+3
+    const int d = min(dl, p.D - 1);
+    uint32_t fx[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) fx[u] = (uint32_t)((p.mic_fx[(size_t)d * 16 + grp * 4 + u] + 0x80000000ull) >> 32);
+    const uint32_t a_row = (uint32_t)row * 128u, a_sw = (uint32_t)(row & 7);
+    const uint32_t b_re = (uint32_t)dl * 128u, b_im = (uint32_t)(TS_BD + dl) * 128u, b_sw = (uint32_t)(dl & 7);
+    const int kp4 = p.KP >> 1;   // float4 (two bins) per spectrum row
+    int stage = 0; uint32_t phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int ks = item / p.n_tt, tt = item - ks * p.n_tt;
+      const int k_begin = ks * p.bins_per_range, k_end = min(p.K, k_begin + p.bins_per_range);
+      const long long t = (long long)tt * TC_BM + row;
+      const bool valid = t < p.BT;
+      const float4 *src = reinterpret_cast<const float4 *>(p.spec + ((valid ? t : 0) * 16 + half * 8) * p.KP);
+      float4 cur[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) cur[u] = valid ? __ldg(src + (size_t)u * kp4 + (k_begin >> 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float cnt = 0.f;
+      for (int k = k_begin; k < k_end; k += 2) {
+        float4 nxt[8];
+        const bool more = (k + 2 < k_end) && valid;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) nxt[u] = more ? __ldg(src + (size_t)u * kp4 + ((k + 2) >> 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          const int kb = k + kk;
+          if (kb < k_end) {
+            float ah[16], al[16];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float2 w = whiten(kk ? make_float2(cur[u].z, cur[u].w) : make_float2(cur[u].x, cur[u].y));
+              cnt += (w.x != 0.f || w.y != 0.f) ? 1.f : 0.f;
+              ah[2 * u] = tf32_hi(w.x); ah[2 * u + 1] = tf32_hi(w.y);
+              al[2 * u] = w.x - ah[2 * u]; al[2 * u + 1] = w.y - ah[2 * u + 1];
+            }
+            float c[4], sn[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int32_t ph = (int32_t)(fx[u] * (uint32_t)kb);
+              __sincosf((float)ph * 1.4629180792671596e-09f, &sn[u], &c[u]);
+            }
+            mbar_wait_bounded(&empty[stage], phase ^ 1);
+            unsigned char *st = smem + stage * TS_STAGE_BYTES;
+            unsigned char *ahp = st + a_row, *alp = st + TS_A_BYTES + a_row;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {   // two microphones = one 16-byte chunk of the frame's row
+              const uint32_t off = ((uint32_t)(half * 4 + q) ^ a_sw) << 4;
+              *reinterpret_cast<float4 *>(ahp + off) = make_float4(ah[4 * q], ah[4 * q + 1], ah[4 * q + 2], ah[4 * q + 3]);
+              *reinterpret_cast<float4 *>(alp + off) = make_float4(al[4 * q], al[4 * q + 1], al[4 * q + 2], al[4 * q + 3]);
+            }
+            unsigned char *bh = st + 2 * TS_A_BYTES, *bl = bh + TS_B_BYTES;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const float ch0 = tf32_hi(c[2 * q]), sh0 = tf32_hi(sn[2 * q]), ch1 = tf32_hi(c[2 * q + 1]), sh1 = tf32_hi(sn[2 * q + 1]);
+              const float cl0 = c[2 * q] - ch0, sl0 = sn[2 * q] - sh0, cl1 = c[2 * q + 1] - ch1, sl1 = sn[2 * q + 1] - sh1;
+              const uint32_t off = ((uint32_t)(grp * 2 + q) ^ b_sw) << 4;
+              *reinterpret_cast<float4 *>(bh + b_re + off) = make_float4(ch0, -sh0, ch1, -sh1);
+              *reinterpret_cast<float4 *>(bh + b_im + off) = make_float4(sh0, ch0, sh1, ch1);
+              *reinterpret_cast<float4 *>(bl + b_re + off) = make_float4(cl0, -sl0, cl1, -sl1);
+              *reinterpret_cast<float4 *>(bl + b_im + off) = make_float4(sl0, cl0, sl1, cl1);
+            }
+            fence_async_smem();
+            mbar_arrive(&full[stage]);
+            if (++stage == TS_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
+      }
+      if (valid && cnt != 0.f) atomicAdd(p.nzsum + t, cnt);   // small integers: the float sum is exact in any order
+    }
+  } else if (warp >= 4 + TC_GEN_THREADS / 32) {
+    // ===== epilogue =====
+    const int e = warp - (4 + TC_GEN_THREADS / 32);
+    const int quarter = warp & 3, half = e >> 2;   // TMEM lanes 32*quarter..+31; directions 32*half..+31
+    constexpr int HD = TS_BD / 2;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int ks = item / p.n_tt, tt = item - ks * p.n_tt;
+      const int k_begin = ks * p.bins_per_range, k_end = min(p.K, k_begin + p.bins_per_range);
+      const long long t = (long long)tt * TC_BM + quarter * 32 + lane;
+      float sum[HD];
+#pragma unroll
+      for (int i = 0; i < HD; ++i) sum[i] = 0.f;
+      for (int k = k_begin; k < k_end; ++k) {
+        mbar_wait_bounded(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 128 + half * HD);
+#pragma unroll
+        for (int j = 0; j < HD / 16; ++j) {
+          float vr[16], vi[16];
+          tmem_ld16(taddr + j * 16, vr);
+          tmem_ld16(taddr + TS_BD + j * 16, vi);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sum[j * 16 + i] = fmaf(vi[i], vi[i], fmaf(vr[i], vr[i], sum[j * 16 + i]));
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (t < p.BT) {
+        const int d0 = half * HD;
+        float *dst = p.partial + (((long long)ks * p.BT + t) * p.D) + d0;
+        const int nd = min(HD, p.D - d0);
+#pragma unroll
+        for (int i = 0; i < HD; ++i) if (i < nd) dst[i] = sum[i];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+}
+
+// work decomposition of the small variant: frame tiles x bin ranges, the range count chosen for full waves of persistent CTAs
+static bool ts_supported(int M, int D) { return M == 16 && D >= 1 && D <= TS_BD; }
+static void ts_plan(long long BT, int N, int D, int sms, TsParams &p) {
+  const int K = N / 2 + 1;
+  p.BT = BT; p.D = D; p.K = K; p.KP = spec_pitch(N);
+  p.n_tt = (int)((BT + TC_BM - 1) / TC_BM);
+  int best_bpr = (K + 1) & ~1;
+  double best_score = -1.0;
+  for (int bpr = 8; bpr <= ((K + 1) & ~1); bpr += 2) {
+    const int n_ks = (K + bpr - 1) / bpr;
+    const long long items = (long long)p.n_tt * n_ks;
+    const long long grid = items < sms ? items : sms;
+    const long long rounds = (items + grid - 1) / grid;
+    // busy fraction of the CTA slots, minus a small charge per work item (pipeline fill, partial map store)
+    const double score = (double)items / (double)(rounds * sms) - 0.004 * (double)n_ks;
+    if (score > best_score) { best_score = score; best_bpr = bpr; }
+  }
+  p.bins_per_range = best_bpr;
+  p.n_ks = (K + best_bpr - 1) / best_bpr;
+}
+static size_t ts_workspace_bytes(long long BT, int N, int D) {
+  auto al = [](size_t n) { return (n + 1023) & ~(size_t)1023; };
+  const int K = N / 2 + 1;
+  return al((size_t)((K + 7) / 8) * BT * D * 4) + al((size_t)BT * 4);   // partial maps for the largest possible range count + nzsum
+}
+static int ts_launch(const float2 *spec, long long BT, int N, const uint64_t *mic_fx, int D, float *srp, void *workspace, size_t ws_bytes,
+                     cudaStream_t st) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  TsParams p;
+  ts_plan(BT, N, D, sms, p);
+  auto al = [](size_t n) { return (n + 1023) & ~(size_t)1023; };
+  const size_t part_bytes = al((size_t)p.n_ks * BT * D * 4);
+  if (part_bytes + al((size_t)BT * 4) > ws_bytes) return mcag_set_error(4, "srp_tensor: workspace too small");
+  unsigned char *w = static_cast<unsigned char *>(workspace);
+  p.spec = spec; p.mic_fx = mic_fx; p.partial = reinterpret_cast<float *>(w); p.nzsum = reinterpret_cast<float *>(w + part_bytes);
+  if (cudaMemsetAsync(p.nzsum, 0, (size_t)BT * 4, st) != cudaSuccess) return mcag_set_cuda_error(cudaGetLastError());
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(srp_tc_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM);
+    cudaFuncSetAttribute(srp_tc_small_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 58);   // 132 KB shared, the rest stays L1
+    attr_set = true;
+  }
+  const long long items = (long long)p.n_tt * p.n_ks;
+  srp_tc_small_kernel<<<(unsigned)(items < sms ? items : sms), TC_THREADS, TS_SMEM, st>>>(p);
+  MCAG_CHECK_LAUNCH();
+  const long long n = BT * D;
+  srp_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.partial, p.n_ks, BT, D, p.nzsum, srp);
+  MCAG_CHECK_LAUNCH();
+  return 0;
+}
+
 // cuTensorMapEncodeTiled is a driver entry point: fetched through the runtime so the library does not link libcuda.so
 // (it must still load, and fail loudly at mcag_create, on a box without a GPU driver).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -448,6 +703,7 @@ bool k_srp_tensor_supported(int M) { return M % 16 == 0 && M >= 16 && M <= 64; }
 // bytes of scratch k_srp_tensor_ws needs for up to BT frames: [U_hi | U_lo | partial | nzsum], each 1 KB aligned
 size_t k_srp_tensor_workspace_bytes(long long BT, int M, int N, int D) {
   if (!k_srp_tensor_supported(M) || BT <= 0) return 0;
+  if (ts_supported(M, D)) return ts_workspace_bytes(BT, N, D);
   TcParams p; long long BTpad;
   tc_plan(BT, M, N, D, p, BTpad);
   auto al = [](size_t n) { return (n + 1023) & ~(size_t)1023; };
@@ -462,6 +718,7 @@ int k_srp_tensor_ws(const float2 *spec, int B, int T, int M, int N, const uint64
   if (B <= 0 || T <= 0) return 0;
   if (!k_srp_tensor_supported(M)) return k_srp_channel(spec, B, T, M, N, mic_fx, D, srp, st);
   const long long BT = (long long)B * T;
+  if (ts_supported(M, D)) return ts_launch(spec, BT, N, mic_fx, D, srp, workspace, ws_bytes, st);
   TcParams p; long long BTpad;
   tc_plan(BT, M, N, D, p, BTpad);
   p.mic_fx = mic_fx;

@@ -360,7 +360,8 @@ def test_host_call_overlapped_stream_groups(mb, dtype):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("M,BT,D,N", [(64, 200, 300, 512), (32, 130, 257, 256), (16, 5, 64, 1024), (48, 128, 128, 512)])
+@pytest.mark.parametrize("M,BT,D,N", [(64, 200, 300, 512), (32, 130, 257, 256), (16, 5, 64, 1024), (48, 128, 128, 512),
+                                      (16, 300, 37, 512), (16, 128, 3, 256), (16, 129, 33, 2048), (16, 20000, 37, 512), (16, 131, 65, 512)])
 def test_srp_tensor_kernel_vs_cuda_core_kernel(mb, M, BT, D, N):
     """K3 on tcgen05 (3xTF32, TMA-fed frames operand, generated steering operand) against the CUDA-core channel-form kernel on
     the same random spectra: partial frame / direction tiles, every supported microphone count, zero bins included."""
