@@ -188,7 +188,9 @@ template <int NKC, bool FAN>   // K chunks per bin = 2M / 32 = M / 16
 __global__ void __launch_bounds__(TC_THREADS, 1) srp_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                                                                 const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1 KB alignment by pointer arithmetic on the __shared__ array itself: an integer round-trip of the pointer loses the address
+  // space and the operand-tile stores become generic ST.E.128 (long-scoreboard WAR stalls in the producers, ncu s4_cfg5_small)
+  unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TC_STAGE_BYTES);
   uint64_t *full_a = bars, *full_b = bars + TC_STAGES, *empty = bars + 2 * TC_STAGES, *tmem_full = bars + 3 * TC_STAGES,
            *tmem_empty = bars + 3 * TC_STAGES + 2;
@@ -428,7 +430,9 @@ struct TsParams {
 
 __global__ void __launch_bounds__(TC_THREADS, 1) srp_tc_small_kernel(const TsParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1 KB alignment by pointer arithmetic on the __shared__ array itself: an integer round-trip of the pointer loses the address
+  // space and the operand-tile stores become generic ST.E.128 (long-scoreboard WAR stalls in the producers, ncu s4_cfg5_small)
+  unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TS_STAGES * TS_STAGE_BYTES);
   uint64_t *full = bars, *empty = bars + TS_STAGES, *tmem_full = bars + 2 * TS_STAGES, *tmem_empty = bars + 2 * TS_STAGES + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TS_STAGES + 4);
