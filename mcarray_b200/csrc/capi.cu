@@ -190,7 +190,8 @@ struct mcag_proc_s {
   DevBuf lags, curves, curve_state, started;
   DevBuf mic_fx, srp_ws;
   DevBuf H, H2, thr, stats, gains, Q, noise, dec, qtrace;
-  DevBuf band_raw, band_energy, floor_pow, band_cells, mb_raw_cell, mb_raw_prob;
+  DevBuf band_raw, band_energy, floor_pow, band_cells, mb_raw_cell, mb_raw_prob, mb_lohi;
+  int mb_bw = 0, mb_kmin = 0, mb_kmax = 0; bool mb_fused = false;   // band supports (host copy of what mb_band_kernel derives from H)
   void *pin_in = nullptr, *pin_out = nullptr; size_t pin_in_bytes = 0, pin_out_bytes = 0;
   std::vector<double> h_window;
   // per-kernel CUDA-event timing (mcag_profile_*): events are recorded on the handle's own stream around each launch
@@ -393,8 +394,22 @@ int mcag_create(const mcag_config *cfg, mcag_proc *out) {
     std::vector<float> H(nb * KP, 0.f);
     for (size_t b = 0; b < nb; ++b) for (int k = 0; k < p->K; ++k) H[b * KP + k] = (float)cfg->band_coefs[b * p->K + k];
     if ((rc = upload(p->H, H.data(), H.size() * 4, st))) return fail(rc);
+    // band supports [lo, hi): first / one-past-last non-zero coefficient, as mb_band_kernel derives them
+    std::vector<int> lohi(2 * nb);
+    p->mb_kmin = p->K; p->mb_kmax = 0; p->mb_bw = 0;
+    for (size_t b = 0; b < nb; ++b) {
+      int lo = p->K, hi = 0;
+      for (int k = 0; k < p->K; ++k) if (H[b * KP + k] != 0.f) { lo = std::min(lo, k); hi = k + 1; }
+      if (hi <= lo) { lo = 0; hi = 0; }   // an all-zero band: empty support
+      lohi[2 * b] = lo; lohi[2 * b + 1] = hi;
+      if (hi > lo) { p->mb_kmin = std::min(p->mb_kmin, lo); p->mb_kmax = std::max(p->mb_kmax, hi); p->mb_bw = std::max(p->mb_bw, hi - lo); }
+    }
+    for (size_t b = 0; b < nb; ++b) if (lohi[2 * b + 1] == 0) lohi[2 * b] = lohi[2 * b + 1] = std::min(p->mb_kmin, p->K - 1);
+    if ((rc = upload(p->mb_lohi, lohi.data(), lohi.size() * sizeof(int), st))) return fail(rc);
+    // MCAG_MB_GENERAL=1 keeps the general three-kernel path (tests compare the two)
+    p->mb_fused = p->mb_kmax > p->mb_kmin && k_mb_fused_supported((int)D, p->mb_bw, p->mb_kmin, p->mb_kmax, (int)nb) && !getenv("MCAG_MB_GENERAL");
     CU(cudaStreamSynchronize(st));
-    if ((rc = p->band_raw.alloc(4 * B * T * nb * D)) || (rc = p->curves.alloc(4 * B * T * nb * D)) || (rc = p->curve_state.alloc(4 * B * nb * D)) ||
+    if ((rc = p->band_raw.alloc(p->mb_fused ? 16 : 4 * B * T * nb * D)) || (rc = p->curves.alloc(4 * B * T * nb * D)) || (rc = p->curve_state.alloc(4 * B * nb * D)) ||
         (rc = p->band_energy.alloc(4 * B * T * nb)) || (rc = p->floor_pow.alloc(4 * B * T)) || (rc = p->energy.alloc(4 * B * T * D)) ||
         (rc = p->band_cells.alloc(4 * B * T * nb)) || (rc = p->mb_raw_cell.alloc(4 * B * T)) || (rc = p->mb_raw_prob.alloc(4 * B * T)) ||
         (rc = p->cells.alloc(4 * B * T)) || (rc = p->prob.alloc(4 * B * T)) || (rc = p->cell_state.alloc(4 * B)))
@@ -453,7 +468,7 @@ void mcag_destroy(mcag_proc p) {
                    &p->active, &p->gate, &p->pair_fx, &p->corr, &p->esum, &p->energy, &p->energy_state, &p->raw_idx, &p->raw_prob, &p->cells,
                    &p->prob, &p->cell_state, &p->prob_state, &p->steer_fx, &p->steer_tab, &p->beams, &p->tail[0], &p->tail[1], &p->out_dev,
                    &p->lags, &p->curves, &p->curve_state, &p->started, &p->mic_fx, &p->srp_ws, &p->H, &p->H2, &p->thr, &p->stats, &p->gains, &p->Q,
-                   &p->noise, &p->dec, &p->qtrace, &p->band_raw, &p->band_energy, &p->floor_pow, &p->band_cells, &p->mb_raw_cell, &p->mb_raw_prob};
+                   &p->noise, &p->dec, &p->qtrace, &p->band_raw, &p->band_energy, &p->floor_pow, &p->band_cells, &p->mb_raw_cell, &p->mb_raw_prob, &p->mb_lohi};
   for (DevBuf *b : all) b->release();
   for (auto &r : p->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (cudaEvent_t e : p->prof_pool) cudaEventDestroy(e);
@@ -670,24 +685,34 @@ static int run_frames(mcag_proc p, const float *x_all, long long pitch, int T, i
     float *band_energy = p->band_energy.as<float>() + o * T * nb_, *floor_pow = p->floor_pow.as<float>() + o * T;
     int32_t *raw_cell = p->mb_raw_cell.as<int32_t>() + o * T;
     float *raw_prob = p->mb_raw_prob.as<float>() + o * T;
-    {
+    if (p->mb_fused) {
       PROF(MCAG_PROF_GCC_TAU);
-      OK(k_mb_band(spec, BT, N, p->H.as<float>(), nb_, p->steer_tab.as<float2>(), D, band_raw, band_energy, floor_pow, st));
+      OK(k_mb_fused(spec, B, T, N, p->H.as<float>(), p->mb_lohi.as<int>(), nb_, p->mb_bw, p->mb_kmin, p->mb_kmax, p->steer_tab.as<float2>(), D,
+                    p->cfg.corr_memory, p->curve_state.as<float>() + o * nb_ * D, curves, band_energy, floor_pow, p->energy.as<float>() + o * T * D,
+                    p->band_cells.as<int32_t>() + o * T * nb_, raw_cell, raw_prob, st));
       p->launches++;
-    }
-    {
-      PROF(MCAG_PROF_CURVE_SCAN);
-      OK(k_mb_scan(band_raw, B, T, nb_, D, p->cfg.corr_memory, p->curve_state.as<float>() + o * nb_ * D, curves, st));
+    } else {
+      {
+        PROF(MCAG_PROF_GCC_TAU);
+        OK(k_mb_band(spec, BT, N, p->H.as<float>(), nb_, p->steer_tab.as<float2>(), D, band_raw, band_energy, floor_pow, st));
+        p->launches++;
+      }
+      {
+        PROF(MCAG_PROF_CURVE_SCAN);
+        OK(k_mb_scan(band_raw, B, T, nb_, D, p->cfg.corr_memory, p->curve_state.as<float>() + o * nb_ * D, curves, st));
+        p->launches++;
+      }
+      PROF(MCAG_PROF_SELECT_DOA);
+      OK(k_mb_summary(curves, band_energy, BT, nb_, D, p->energy.as<float>() + o * T * D, p->band_cells.as<int32_t>() + o * T * nb_, raw_cell, raw_prob, st));
       p->launches++;
     }
     {
       PROF(MCAG_PROF_SELECT_DOA);
-      OK(k_mb_summary(curves, band_energy, BT, nb_, D, p->energy.as<float>() + o * T * D, p->band_cells.as<int32_t>() + o * T * nb_, raw_cell, raw_prob, st));
       const int needed = (int)(p->cfg.floor_seconds * (float)p->cfg.sample_rate);
       OK(k_mb_gate(floor_pow, chan_pow, raw_cell, raw_prob, B, T, N, p->cfg.use_power_floor, p->cfg.noise_margin_db, needed,
                    p->gate.as<GateState>() + o, p->cell_state.as<int32_t>() + o, p->power_db.as<float>() + o * T, active,
                    p->cells.as<int32_t>() + o * T, p->prob.as<float>() + o * T, st));
-      p->launches += 2;
+      p->launches++;
     }
   } else if (kind == MCAG_KIND_DSFAN) {
     PROF(MCAG_PROF_DS_FAN);

@@ -56,6 +56,10 @@ int k_mask_apply(float2 *spec, long long BT, int N, const float *H, int nb, cons
 // multiband.cu
 int k_mb_band(const float2 *spec, long long BT, int N, const float *H, int nb, const float2 *W, int D, float *band_raw, float *band_energy,
               float *floor_pow, cudaStream_t st);
+bool k_mb_fused_supported(int D, int max_band_width, int kmin, int kmax, int nb);
+int k_mb_fused(const float2 *spec, int B, int T, int N, const float *H, const int *band_lohi, int nb, int max_band_width, int kmin, int kmax,
+               const float2 *W, int D, float mem, float *state, float *curves, float *band_energy, float *floor_pow, float *hist,
+               int32_t *band_cells, int32_t *raw_cell, float *raw_prob, cudaStream_t st);
 int k_mb_scan(const float *raw, int B, int T, int nb, int D, float mem, float *state, float *curves, cudaStream_t st);
 int k_mb_summary(const float *curves, const float *band_energy, long long BT, int nb, int D, float *hist, int32_t *band_cells, int32_t *raw_cell,
                  float *raw_prob, cudaStream_t st);
