@@ -262,6 +262,39 @@ def test_multiband_gate_and_streams_vs_oracle(mb, orc):
         assert np.array_equal(bcells[b][on], ref["band_cells"])
 
 
+def test_multiband_general_path_equals_fused_path(mb):
+    """the fused band / scan / summary kernel (D <= 64, bands <= 16 bins) and the general three-kernel path (MCAG_MB_GENERAL=1) on
+    the same streams, ragged chunks: cells, band cells and gate decisions identical, curves / histogram / prob within tolerance"""
+    fs, d, B = 16000, 0.089, 5
+    xyz = scenes.linear_array([0, d])
+    X = np.stack([scenes.far_field_scene(xyz, fs, fs + 777, scenes.azimuth_dirs([np.deg2rad(-60 + 30 * b)]), seed=scenes.stream_seed(70 + b))
+                  for b in range(B)]).astype(np.float32)
+    flat = X.reshape(B * 2, -1)
+
+    def run(general):
+        if general:
+            os.environ["MCAG_MB_GENERAL"] = "1"
+        try:
+            p = mb.MultibandBinarualLocalisation(fs, d, nbins=15, usePowerFloor=False, n_streams=B, max_frames_per_call=80)
+        finally:
+            os.environ.pop("MCAG_MB_GENERAL", None)
+        out = {k: [] for k in ("cells", "band_cells", "curves", "hist", "prob")}
+        for pos in range(0, flat.shape[1], 7001):
+            p.process(flat[:, pos:pos + 7001])
+            if p.frames_done:
+                out["cells"].append(p.cells()); out["band_cells"].append(p.band_cells()); out["hist"].append(p.histogram())
+                out["prob"].append(p.prob()); out["curves"].append(p.band_curves())
+        p.close()
+        return {k: np.concatenate(v, axis=1) for k, v in out.items()}
+
+    a, b = run(False), run(True)
+    assert a["cells"].shape[1] > 100
+    assert np.array_equal(a["cells"], b["cells"]) and np.array_equal(a["band_cells"], b["band_cells"])
+    assert_close(a["curves"], b["curves"], (3,), "band curves")
+    assert_close(a["hist"], b["hist"], (2,), "energy histogram")
+    assert np.allclose(a["prob"], b["prob"], rtol=1e-4, atol=1e-6)
+
+
 @pytest.mark.parametrize("name,method", [("full", "FULL"), ("relative", "RELATIVE"), ("factor", "FACTOR"), ("noisy", "NOISY")])
 def test_mask_against_reference_golden(mb, name, method):
     g = np.load(os.path.join(G, "mask_spatial_16k.npz"))
