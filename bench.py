@@ -131,7 +131,9 @@ class Cfg5(Workload):
     def kernel_bytes_per_frame(self):
         M, hop, K, P, D = self.M, self.hop, self.N // 2 + 1, self.M * (self.M - 1) // 2, 37
         return {"stft": 4 * M * hop + 8 * M * K, "gcc_tau": 8 * M * K + 4 * P * D, "energy": 4 * P * D + 4 * D, "select_doa": 4 * D + 8,
-                "ds_select": 8 * M * K + 8 * K, "istft": 8 * K + 4 * hop}
+                "ds_select": 8 * M * K + 8 * K, "istft": 8 * K + 4 * hop,
+                # channel-form SRP on tcgen05 (srp_tc_small_kernel): reads the M spectra once, writes the D-cell energy map
+                "srp": 8 * M * K + 4 * D}
 
     def pipeline_bytes_per_frame(self):
         return 4 * self.M * self.hop + 4 * (self.M * (self.M - 1) // 2) + 4 * self.hop   # 17 888 B

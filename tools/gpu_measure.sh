@@ -9,7 +9,7 @@ for w in cfg2 cfg5 cfg4 cfg1m cfg1l cfg1b cfg3; do
   timeout 600 python bench.py --workload $w $extra > $O/${R}_bench_$w.json 2> $O/${R}_bench_$w.err
   tail -c 400 $O/${R}_bench_$w.json; echo
 done
-for w in cfg2 cfg5 cfg4 cfg1m cfg1b cfg3; do
+for w in cfg2 cfg5 cfg4 cfg1m cfg1b cfg1l cfg3; do
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${R}_${w}_launches.csv \
     python bench.py --workload $w --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>&1
 done
@@ -18,9 +18,10 @@ cap() {  # workload, kernel regex, skip, count, tag
     python bench.py --workload $1 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>&1
 }
 cap cfg2 stft_tdoa_kernel 3 1 cfg2_stft_tdoa
-cap cfg5 "srp_tc_kernel|srp_prepare_kernel|ds_select_kernel" 9 3 cfg5_srp
+cap cfg5 "srp_tc_small_kernel|ds_select_kernel|stft_kernel" 9 3 cfg5_srp
 cap cfg4 "srp_tc_kernel" 3 1 cfg4_srp_tc
 cap cfg3 "ds_fan_kernel" 3 1 cfg3_ds_fan
 cap cfg1m "stft_kernel|istft_kernel|mask_stats_kernel|mask_apply_kernel" 12 4 cfg1m_kernels
-cap cfg1b "mb_band_kernel|mb_summary_kernel" 6 2 cfg1b_kernels
+cap cfg1b "mb_fused_kernel|mb_gate_kernel" 6 2 cfg1b_kernels
+cap cfg1l "gcc_tau_kernel|curve_scan" 6 2 cfg1l_kernels
 ls -la $O | tail -30
