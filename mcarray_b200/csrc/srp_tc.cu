@@ -98,6 +98,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
@@ -416,6 +427,9 @@ constexpr int TS_A_BYTES = TC_BM * TC_KC * 4;          // 16 KB
 constexpr int TS_B_BYTES = 2 * TS_BD * TC_KC * 4;      // 16 KB
 constexpr int TS_STAGE_BYTES = 2 * TS_A_BYTES + 2 * TS_B_BYTES;   // 64 KB
 constexpr int TS_SMEM = TS_STAGES * TS_STAGE_BYTES + 1024 + 256;
+// warp 0: MMA issuer; warps 1-16: 512 producer threads (the operand build is the critical path: 16 warps hide its latencies where 8
+// ran at 0.43 IPC); warps 17-24: epilogue (any 4 consecutive warps cover the four TMEM lane quarters)
+constexpr int TS_PROD_THREADS = 512, TS_EPI_THREADS = 256, TS_THREADS = 32 + TS_PROD_THREADS + TS_EPI_THREADS;
 constexpr uint32_t TS_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
 struct TsParams {
@@ -428,7 +442,7 @@ struct TsParams {
   float *nzsum;                     // [BT], zeroed before the launch
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1) srp_tc_small_kernel(const TsParams p) {
+__global__ void __launch_bounds__(TS_THREADS, 1) srp_tc_small_kernel(const TsParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1 KB alignment by pointer arithmetic on the __shared__ array itself: an integer round-trip of the pointer loses the address
   // space and the operand-tile stores become generic ST.E.128 (long-scoreboard WAR stalls in the producers, ncu s4_cfg5_small)
@@ -439,10 +453,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) srp_tc_small_kernel(const TsPar
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < TS_STAGES; ++s) { mbar_init(&full[s], TC_GEN_THREADS); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], TC_EPI_THREADS); }
+    for (int s = 0; s < TS_STAGES; ++s) { mbar_init(&full[s], TS_PROD_THREADS); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], TS_EPI_THREADS); }
   }
-  if (warp == 1) {
+  if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -452,7 +466,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) srp_tc_small_kernel(const TsPar
   const uint32_t tmem_base = *tmem_slot;
   const int n_items = p.n_tt * p.n_ks;
 
-  if (warp == 1) {
+  if (warp == 0) {
     // ===== MMA issuer =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
@@ -481,15 +495,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) srp_tc_small_kernel(const TsPar
         }
       }
     }
-  } else if (warp >= 4 && warp < 4 + TC_GEN_THREADS / 32) {
+  } else if (warp <= TS_PROD_THREADS / 32) {
     // ===== producers: frames operand from the spectra + generated steering operand =====
-    const int g = tid - 128;
-    const int row = g & (TC_BM - 1), half = g >> 7;   // frames operand: frame row of the tile, microphones 8*half .. 8*half+7
-    const int dl = g & (TS_BD - 1), grp = g >> 6;     // steering operand: direction, microphones 4*grp .. 4*grp+3
+    const int g = tid - 32;
+    const int row = g & (TC_BM - 1), qm = g >> 7;     // frames operand: frame row of the tile, microphones 4*qm .. 4*qm+3
+    const int dl = g & (TS_BD - 1), grp = g >> 6;     // steering operand: direction, microphones 2*grp, 2*grp+1
     const int d = min(dl, p.D - 1);
-    uint32_t fx[4];
+    uint32_t fx[2];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) fx[u] = (uint32_t)((p.mic_fx[(size_t)d * 16 + grp * 4 + u] + 0x80000000ull) >> 32);
+    for (int u = 0; u < 2; ++u) fx[u] = (uint32_t)((p.mic_fx[(size_t)d * 16 + grp * 2 + u] + 0x80000000ull) >> 32);
     const uint32_t a_row = (uint32_t)row * 128u, a_sw = (uint32_t)(row & 7);
     const uint32_t b_re = (uint32_t)dl * 128u, b_im = (uint32_t)(TS_BD + dl) * 128u, b_sw = (uint32_t)(dl & 7);
     const int kp4 = p.KP >> 1;   // float4 (two bins) per spectrum row
@@ -499,31 +513,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) srp_tc_small_kernel(const TsPar
       const int k_begin = ks * p.bins_per_range, k_end = min(p.K, k_begin + p.bins_per_range);
       const long long t = (long long)tt * TC_BM + row;
       const bool valid = t < p.BT;
-      const float4 *src = reinterpret_cast<const float4 *>(p.spec + ((valid ? t : 0) * 16 + half * 8) * p.KP);
-      float4 cur[8];
+      const float4 *src = reinterpret_cast<const float4 *>(p.spec + ((valid ? t : 0) * 16 + qm * 4) * p.KP);
+      float4 cur[4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) cur[u] = valid ? __ldg(src + (size_t)u * kp4 + (k_begin >> 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int u = 0; u < 4; ++u) cur[u] = valid ? __ldg(src + (size_t)u * kp4 + (k_begin >> 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
       float cnt = 0.f;
       for (int k = k_begin; k < k_end; k += 2) {
-        float4 nxt[8];
+        float4 nxt[4];
         const bool more = (k + 2 < k_end) && valid;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) nxt[u] = more ? __ldg(src + (size_t)u * kp4 + ((k + 2) >> 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 0; u < 4; ++u) nxt[u] = more ? __ldg(src + (size_t)u * kp4 + ((k + 2) >> 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk) {
           const int kb = k + kk;
           if (kb < k_end) {
-            float ah[16], al[16];
+            float ah[8], al[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < 4; ++u) {
               const float2 w = whiten(kk ? make_float2(cur[u].z, cur[u].w) : make_float2(cur[u].x, cur[u].y));
               cnt += (w.x != 0.f || w.y != 0.f) ? 1.f : 0.f;
               ah[2 * u] = tf32_hi(w.x); ah[2 * u + 1] = tf32_hi(w.y);
               al[2 * u] = w.x - ah[2 * u]; al[2 * u + 1] = w.y - ah[2 * u + 1];
             }
-            float c[4], sn[4];
+            float c[2], sn[2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 2; ++u) {
               const int32_t ph = (int32_t)(fx[u] * (uint32_t)kb);
               __sincosf((float)ph * 1.4629180792671596e-09f, &sn[u], &c[u]);
             }
@@ -531,17 +545,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) srp_tc_small_kernel(const TsPar
             unsigned char *st = smem + stage * TS_STAGE_BYTES;
             unsigned char *ahp = st + a_row, *alp = st + TS_A_BYTES + a_row;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {   // two microphones = one 16-byte chunk of the frame's row
-              const uint32_t off = ((uint32_t)(half * 4 + q) ^ a_sw) << 4;
+            for (int q = 0; q < 2; ++q) {   // two microphones = one 16-byte chunk of the frame's row
+              const uint32_t off = ((uint32_t)(qm * 2 + q) ^ a_sw) << 4;
               *reinterpret_cast<float4 *>(ahp + off) = make_float4(ah[4 * q], ah[4 * q + 1], ah[4 * q + 2], ah[4 * q + 3]);
               *reinterpret_cast<float4 *>(alp + off) = make_float4(al[4 * q], al[4 * q + 1], al[4 * q + 2], al[4 * q + 3]);
             }
             unsigned char *bh = st + 2 * TS_A_BYTES, *bl = bh + TS_B_BYTES;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
+            {
+              constexpr int q = 0;
               const float ch0 = tf32_hi(c[2 * q]), sh0 = tf32_hi(sn[2 * q]), ch1 = tf32_hi(c[2 * q + 1]), sh1 = tf32_hi(sn[2 * q + 1]);
               const float cl0 = c[2 * q] - ch0, sl0 = sn[2 * q] - sh0, cl1 = c[2 * q + 1] - ch1, sl1 = sn[2 * q + 1] - sh1;
-              const uint32_t off = ((uint32_t)(grp * 2 + q) ^ b_sw) << 4;
+              const uint32_t off = ((uint32_t)grp ^ b_sw) << 4;
               *reinterpret_cast<float4 *>(bh + b_re + off) = make_float4(ch0, -sh0, ch1, -sh1);
               *reinterpret_cast<float4 *>(bh + b_im + off) = make_float4(sh0, ch0, sh1, ch1);
               *reinterpret_cast<float4 *>(bl + b_re + off) = make_float4(cl0, -sl0, cl1, -sl1);
@@ -553,13 +567,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) srp_tc_small_kernel(const TsPar
           }
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
+        for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
       }
       if (valid && cnt != 0.f) atomicAdd(p.nzsum + t, cnt);   // small integers: the float sum is exact in any order
     }
-  } else if (warp >= 4 + TC_GEN_THREADS / 32) {
+  } else {
     // ===== epilogue =====
-    const int e = warp - (4 + TC_GEN_THREADS / 32);
+    const int e = warp - (1 + TS_PROD_THREADS / 32);
     const int quarter = warp & 3, half = e >> 2;   // TMEM lanes 32*quarter..+31; directions 32*half..+31
     constexpr int HD = TS_BD / 2;
     int acc = 0; uint32_t acc_phase = 0;
@@ -575,12 +589,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) srp_tc_small_kernel(const TsPar
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 128 + half * HD);
 #pragma unroll
-        for (int j = 0; j < HD / 16; ++j) {
-          float vr[16], vi[16];
-          tmem_ld16(taddr + j * 16, vr);
-          tmem_ld16(taddr + TS_BD + j * 16, vi);
+        for (int j = 0; j < HD / 8; ++j) {   // 8 columns at a time: the 800-thread CTA leaves 72 registers per thread
+          float vr[8], vi[8];
+          tmem_ld8(taddr + j * 8, vr);
+          tmem_ld8(taddr + TS_BD + j * 8, vi);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) sum[j * 16 + i] = fmaf(vi[i], vi[i], fmaf(vr[i], vr[i], sum[j * 16 + i]));
+          for (int i = 0; i < 8; ++i) sum[j * 8 + i] = fmaf(vi[i], vi[i], fmaf(vr[i], vr[i], sum[j * 8 + i]));
         }
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);
@@ -597,7 +611,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) srp_tc_small_kernel(const TsPar
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
 }
 
 // work decomposition of the small variant: frame tiles x bin ranges, the range count chosen for full waves of persistent CTAs
@@ -645,7 +659,7 @@ static int ts_launch(const float2 *spec, long long BT, int N, const uint64_t *mi
     attr_set = true;
   }
   const long long items = (long long)p.n_tt * p.n_ks;
-  srp_tc_small_kernel<<<(unsigned)(items < sms ? items : sms), TC_THREADS, TS_SMEM, st>>>(p);
+  srp_tc_small_kernel<<<(unsigned)(items < sms ? items : sms), TS_THREADS, TS_SMEM, st>>>(p);
   MCAG_CHECK_LAUNCH();
   const long long n = BT * D;
   srp_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.partial, p.n_ks, BT, D, p.nzsum, srp);
