@@ -516,13 +516,15 @@ __global__ void __launch_bounds__(TS_THREADS, 1) srp_tc_small_kernel(const TsPar
       const float4 *src = reinterpret_cast<const float4 *>(p.spec + ((valid ? t : 0) * 16 + qm * 4) * p.KP);
       float4 cur[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) cur[u] = valid ? __ldg(src + (size_t)u * kp4 + (k_begin >> 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int u = 0; u < 4; ++u) cur[u] = __ldg(src + (size_t)u * kp4 + (k_begin >> 1));   // rows past BT read frame 0 and are zeroed below
       float cnt = 0.f;
       for (int k = k_begin; k < k_end; k += 2) {
         float4 nxt[4];
-        const bool more = (k + 2 < k_end) && valid;
+        // always a load (the last pair of a range re-reads itself): a select against zero made the compiler clear the destination
+        // registers first, and that write waited on the address reads of the loads still queued in the LSU (ncu s4_cfg5_small2)
+        const int kn = (k + 2 < k_end) ? k + 2 : k;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) nxt[u] = more ? __ldg(src + (size_t)u * kp4 + ((k + 2) >> 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 0; u < 4; ++u) nxt[u] = __ldg(src + (size_t)u * kp4 + (kn >> 1));
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk) {
           const int kb = k + kk;
@@ -530,7 +532,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) srp_tc_small_kernel(const TsPar
             float ah[8], al[8];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              const float2 w = whiten(kk ? make_float2(cur[u].z, cur[u].w) : make_float2(cur[u].x, cur[u].y));
+              float2 w = whiten(kk ? make_float2(cur[u].z, cur[u].w) : make_float2(cur[u].x, cur[u].y));
+              if (!valid) w = make_float2(0.f, 0.f);
               cnt += (w.x != 0.f || w.y != 0.f) ? 1.f : 0.f;
               ah[2 * u] = tf32_hi(w.x); ah[2 * u + 1] = tf32_hi(w.y);
               al[2 * u] = w.x - ah[2 * u]; al[2 * u + 1] = w.y - ah[2 * u + 1];
@@ -655,7 +658,7 @@ static int ts_launch(const float2 *spec, long long BT, int N, const uint64_t *mi
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(srp_tc_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM);
-    cudaFuncSetAttribute(srp_tc_small_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 58);   // 132 KB shared, the rest stays L1
+    cudaFuncSetAttribute(srp_tc_small_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 58);   // 132 KB shared, ~96 KB stay L1 (3 stages / no L1: 0.57 ms instead of 0.31)
     attr_set = true;
   }
   const long long items = (long long)p.n_tt * p.n_ks;
