@@ -655,12 +655,9 @@ static int ts_launch(const float2 *spec, long long BT, int N, const uint64_t *mi
   unsigned char *w = static_cast<unsigned char *>(workspace);
   p.spec = spec; p.mic_fx = mic_fx; p.partial = reinterpret_cast<float *>(w); p.nzsum = reinterpret_cast<float *>(w + part_bytes);
   if (cudaMemsetAsync(p.nzsum, 0, (size_t)BT * 4, st) != cudaSuccess) return mcag_set_cuda_error(cudaGetLastError());
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(srp_tc_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM);
-    cudaFuncSetAttribute(srp_tc_small_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 58);   // 132 KB shared, ~96 KB stay L1 (3 stages / no L1: 0.57 ms instead of 0.31)
-    attr_set = true;
-  }
+  // per launch, like launch_tc: function attributes are per device and a process may drive more than one
+  cudaFuncSetAttribute(srp_tc_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM);
+  cudaFuncSetAttribute(srp_tc_small_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 58);   // 132 KB shared, ~96 KB stay L1 (3 stages / no L1: 0.57 ms instead of 0.31)
   const long long items = (long long)p.n_tt * p.n_ks;
   srp_tc_small_kernel<<<(unsigned)(items < sms ? items : sms), TS_THREADS, TS_SMEM, st>>>(p);
   MCAG_CHECK_LAUNCH();
