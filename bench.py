@@ -337,7 +337,14 @@ class Cfg3(Workload):
         return B * T * self.D * p.info.spectrum_pitch * 8
 
     def fetch_result(self, p):
-        return p.fetch(9, (p.info.n_streams, p.frames_done, self.D, p.info.spectrum_pitch))   # MCAG_OUT_BEAMS
+        # MCAG_OUT_BEAMS (760 MB per step) into a pinned buffer kept across steps: a fresh pageable array per step cost 150 ms
+        import torch
+        from mcarray_b200 import capi
+        nbytes = self.result_bytes(p, p.info.n_streams, p.frames_done)
+        if getattr(self, "_pin", None) is None or self._pin.numel() < nbytes:
+            self._pin = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        capi.check(capi.lib().mcag_fetch(p.handle, 9, C.c_void_p(self._pin.data_ptr()), C.c_longlong(nbytes)))
+        return self._pin
 
     def kernel_bytes_per_frame(self):
         M, hop, K, D = self.M, self.hop, self.N // 2 + 1, self.D
@@ -463,7 +470,9 @@ def main():
     ap.add_argument("--cpu-streams-per-core", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-s16", action="store_true", help="also time the end-to-end path with int16 PCM host buffers (extra key e2e_s16)")
+    ap.add_argument("--e2e-s16", action="store_true", default=None,
+                    help="also time the end-to-end path with int16 PCM host buffers (extra key e2e_s16); default: on at N = 1 for cfg2")
+    ap.add_argument("--no-e2e-s16", dest="e2e_s16", action="store_false")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3 if args.impl == "b200" else max(args.warmup, 1)
@@ -596,6 +605,8 @@ def main():
 
     # ---- e2e with 16-bit PCM host buffers (the int16 overload of process(), test_mcarray.cpp:937): half the PCIe bytes ----------------
     e2e_s16 = None
+    if args.e2e_s16 is None:
+        args.e2e_s16 = world == 1 and args.workload == "cfg2"
     if not args.no_e2e and not sharded and args.e2e_s16:
         pin16 = torch.empty((rows, n), dtype=torch.int16).pin_memory()
         pin16.copy_(pin.round().clamp_(-32768, 32767).to(torch.int16))
