@@ -21,8 +21,38 @@ __host__ __device__ constexpr int spec_pitch(int N) { return N / 2 + 2; }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a*conj(b)
+#ifndef MCAG_NO_F32X2
+// packed fp32 (FADD2, sm_100): one issue slot for both components (tools/ubench/f32x2.cu: same lane rate, half the instructions).
+// The FFT kernels are issue / shared-memory bound, so this is worth 2.5 % on the fused STFT -> GCC-PHAT kernel (tools/variants.sh).
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+  unsigned long long pa, pb, pr; float2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pa) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(pr) : "l"(pa), "l"(pb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(pr));
+  return r;
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+  unsigned long long pa, pb, pr; float2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pa) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pb) : "f"(b.x), "f"(b.y));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(pr) : "l"(pa), "l"(pb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(pr));
+  return r;
+}
+__device__ __forceinline__ float2 cscale(float2 a, float s_) {
+  unsigned long long pa, ps, pr; float2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pa) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ps) : "f"(s_));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(pr) : "l"(pa), "l"(ps));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(pr));
+  return r;
+}
+#else
+__device__ __forceinline__ float2 cscale(float2 a, float s_) { return make_float2(a.x * s_, a.y * s_); }
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 
 // PHAT whitening of one bin: X/|X|, 0 where |X| = 0 (oracle/CONVENTIONS.md C5)

@@ -37,12 +37,15 @@ __device__ __forceinline__ void pair_table(unsigned char *s_pair, int M, int P, 
   }
 }
 
-// E/O twiddles conj(W_N^k) of the packed inverse real transform for the 4 bins k = j + r*TPF (r < 4) this thread builds: the
+// E/O twiddles i * conj(W_N^k) of the packed inverse real transform for the 4 bins k = j + r*TPF (r < 4) this thread builds: the
 // same for every pair and frame, so they live in registers
 template <int N> __device__ __forceinline__ void load_eo_twiddles(const float2 *s_tw, int j, float2 (&wk)[4]) {
   constexpr int NC = N / 2, TPF = NC / 8;
 #pragma unroll
-  for (int r = 0; r < 4; ++r) wk[r] = tw_lookup<true>(s_tw, j + r * TPF, NC);
+  for (int r = 0; r < 4; ++r) {   // stored times i: the build then forms E + iO and conj(E - iO) with packed adds only
+    const float2 w = tw_lookup<true>(s_tw, j + r * TPF, NC);
+    wk[r] = make_float2(-w.y, w.x);
+  }
 }
 
 // all P pairs of the frame whose whitened spectra are in s_U; every thread of the CTA calls it (uniform trip count).
@@ -75,13 +78,12 @@ __device__ __forceinline__ void tdoa_pairs(const float2 *s_U, const float2 (&wk)
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int k = j + r * TPF;
-      float2 gk = cmulc(Ui[k], Uj[k]), gn = cmulc(Ui[NC - k], Uj[NC - k]);
-      if (k == 0) { gk.y = 0.f; gn.y = 0.f; }
-      float2 e = make_float2(0.5f * (gk.x + gn.x), 0.5f * (gk.y - gn.y));
-      float2 d = make_float2(0.5f * (gk.x - gn.x), 0.5f * (gk.y + gn.y));
-      float2 o = cmul(d, wk[r]);
-      v[r] = make_float2(e.x - o.y, e.y + o.x);
-      const float2 zn = make_float2(e.x + o.y, o.x - e.y);
+      float2 gk = cmulc(Ui[k], Uj[k]), gc = cmulc(Uj[NC - k], Ui[NC - k]);   // G[k] and conj(G[NC-k])
+      if (k == 0) { gk.y = 0.f; gc.y = 0.f; }
+      const float2 e = cscale(cadd(gk, gc), 0.5f), d = cscale(csub(gk, gc), 0.5f);
+      const float2 o = cmul(d, wk[r]);               // i * O[k]
+      v[r] = cadd(e, o);                             // Z[k] = E + iO
+      const float2 zn = cconj(csub(e, o));           // Z[NC-k] = conj(E - iO)
       if (j != 0) sts64(buf ^ (8u * (uint32_t)fft_pad(8 * pj + 7 - r)), zn);
       else if (r != 0) sts64(buf ^ (8u * (uint32_t)fft_pad(8 - r)), zn);
     }

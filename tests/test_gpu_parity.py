@@ -267,7 +267,7 @@ def test_multiband_general_path_equals_fused_path(mb):
     the same streams, ragged chunks: cells, band cells and gate decisions identical, curves / histogram / prob within tolerance"""
     fs, d, B = 16000, 0.089, 5
     xyz = scenes.linear_array([0, d])
-    X = np.stack([scenes.far_field_scene(xyz, fs, fs + 777, scenes.azimuth_dirs([np.deg2rad(-60 + 30 * b)]), seed=scenes.stream_seed(70 + b))
+    X = np.stack([scenes.far_field_scene(xyz, fs, 2 * fs + 777, scenes.azimuth_dirs([np.deg2rad(-60 + 30 * b)]), seed=scenes.stream_seed(70 + b))
                   for b in range(B)]).astype(np.float32)
     flat = X.reshape(B * 2, -1)
 
