@@ -82,11 +82,16 @@ __global__ void curve_scan_kernel(const float *__restrict__ corr, int B, int T, 
   const int b = i / D, d = i - b * D;
   float prev = state[i];
   bool started = started_in[b] != 0;
+  // only `prev` and `started` are carried: the loads are unconditional and the loop is unrolled so that eight frames of inputs are in
+  // flight per thread (one frame at a time the kernel was bound by the latency of its dependent loads)
+#pragma unroll 8
   for (int t = 0; t < T; ++t) {
     const long long o = ((long long)b * T + t) * D + d;
-    if (!active || active[(long long)b * T + t]) {
+    const float c = corr[o];
+    const bool on = !active || active[(long long)b * T + t];
+    if (on) {
       const float alpha = started ? mem : 0.f;
-      prev = (1.f - alpha) * corr[o] + alpha * prev;
+      prev = (1.f - alpha) * c + alpha * prev;
       started = true;
     }
     curves[o] = prev;
