@@ -147,3 +147,22 @@ def test_multiband_golden(orc):
         assert np.array_equal(r[k], g[k]), k
     # the source moves from +35 to -20 degrees: the published cells follow it (5 degree grid, cell = (deg + 90) / 5)
     assert np.median(g["cell"][5:25]) == 25 and np.median(g["cell"][-20:]) == 14
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU arm the driver runs beside the GPU arm) on a tiny sample: one JSON line with the contract keys,
+    no CUDA needed"""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-frames", "8", "--cpu-streams-per-core", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "impl", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data",
+                "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["metric"] == "channel_samples_per_sec" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
