@@ -68,8 +68,10 @@ enum {
   MCAG_OUT_BEAMS = 9,     /* float2 [B][T][C][N/2+2]  beamformed / masked spectra (SSL, MASK, DSFAN: C = D) */
   MCAG_OUT_MASK_Q = 10,   /* float  [B][T][nb]        short-time band power after each frame (MASK) */
   MCAG_OUT_MASK_DEC = 11, /* uint8  [B][T][nb]        2 = spatial mask, 1 = temporal mask, 0 = pass (MASK) */
-  MCAG_OUT_BAND_CELL = 12 /* int32  [B][T][nb]        arg-max cell of each sub-band curve (MULTIBAND); its MCAG_OUT_CURVES is [B][T][nb][D],
+  MCAG_OUT_BAND_CELL = 12,/* int32  [B][T][nb]        arg-max cell of each sub-band curve (MULTIBAND); its MCAG_OUT_CURVES is [B][T][nb][D],
                              MCAG_OUT_ENERGY the energy-weighted histogram [B][T][D], MCAG_OUT_CELL / _PROB [B][T] */
+  MCAG_OUT_TRACK_DOA = 13 /* double [B][T]            FREQGCC with doa_tracker: _currentDOA (rad) after each frame, the deterministic
+                             `#else` branch of BinauralLocalisation.cpp:501-504; its MCAG_OUT_PROB [B][T] is setProbability (:454,569-631) */
 };
 
 enum {                    /* emit flags: keep optional intermediates of the last call fetchable */
@@ -119,6 +121,12 @@ typedef struct {
    * 1 pair form always (pair by pair in the reference's order; MCAG_OUT_CORR is only produced by this form).
    * 2 channel form required: mcag_create fails if the geometry / channel count does not allow it. */
   int srp_form;
+
+  /* FREQGCC: deterministic DOA tracker replacing the (stochastic, out-of-scope) particle filter: the `#else` branch of
+   * USE_PARTICLE_FILTER, _currentDOA = m _currentDOA + (1-m) DOA with m = _doaMemoryFactor (0 -> doa_memory after a voiced frame, 0 after
+   * 3 s of silence; BinauralLocalisation.cpp:502-504,523-524,528-561) and setProbability (:569-631).  0 = off (arg-max cell only). */
+  int doa_tracker;
+  float doa_memory;       /* 0.6f: _maxDoaMemoryFactor, BinauralLocalisation.h:199 */
 } mcag_config;
 
 typedef struct {

@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("MCAG_LIB_PATH") or os.path.join(_HERE, "libmcarray_b2
 
 KIND_SSL, KIND_SL, KIND_FREQGCC, KIND_MASK, KIND_TDOA, KIND_DSFAN, KIND_SRP, KIND_MULTIBAND = range(8)
 (OUT_SPECTRA, OUT_POWER_DB, OUT_CORR, OUT_ENERGY, OUT_CELL, OUT_PROB, OUT_LAGS, OUT_CURVES, OUT_ACTIVE, OUT_BEAMS,
- OUT_MASK_Q, OUT_MASK_DEC, OUT_BAND_CELL) = range(13)
+ OUT_MASK_Q, OUT_MASK_DEC, OUT_BAND_CELL, OUT_TRACK_DOA) = range(14)
 EMIT_CORR, EMIT_CURVES, EMIT_SPECTRA = 1, 2, 4
 
 c_dp = C.POINTER(C.c_double)
@@ -24,7 +24,7 @@ class Config(C.Structure):
         ("energy_memory", C.c_float), ("corr_memory", C.c_float), ("use_power_floor", C.c_int), ("noise_margin_db", C.c_float),
         ("floor_seconds", C.c_float), ("floor_ccs_power", C.c_int), ("noise_preestimated", C.c_int), ("max_lag", C.c_int),
         ("mask_method", C.c_int), ("mask_alg", C.c_int), ("n_bands", C.c_int), ("band_coefs", c_dp), ("band_thresholds", c_dp),
-        ("srp_form", C.c_int),
+        ("srp_form", C.c_int), ("doa_tracker", C.c_int), ("doa_memory", C.c_float),
     ]
 
 

@@ -46,7 +46,8 @@ struct GateState { double acc; double floor; int samples; int estimated; };
 
 __global__ void __launch_bounds__(256) gate_kernel(const float *__restrict__ chan_pow, const float *__restrict__ chan_raw, int B, int T, int M, int N,
                                                    int use_floor, int ccs_mode, float margin_db, int needed, GateState *__restrict__ gs,
-                                                   float *__restrict__ power_db, unsigned char *__restrict__ active) {
+                                                   float *__restrict__ power_db, unsigned char *__restrict__ active,
+                                                   unsigned char *__restrict__ est /* optional: _noiseEstimated after the frame's floor update */) {
   // one CTA per stream: thread 0 walks the frames that still feed the noise-floor estimate (a strictly sequential
   // accumulation, at most floor_seconds of audio per stream), then all threads gate the remaining frames in parallel.
   __shared__ GateState s_state;
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(256) gate_kernel(const float *__restrict__ cha
       s.floor = s.acc;
       power_db[(long long)b * T + t] = (float)s.floor;
       active[(long long)b * T + t] = use_floor ? 0 : 1;   // power == floor here, so `power > floor` is false
+      if (est) est[(long long)b * T + t] = (unsigned char)s.estimated;   // the frame that completes the estimate already counts as silent (:528)
     }
     gs[b] = s;
     s_state = s;
@@ -91,6 +93,7 @@ __global__ void __launch_bounds__(256) gate_kernel(const float *__restrict__ cha
     const double power = 10.0 * log10(lin / (double)M);
     power_db[(long long)b * T + t] = (float)power;
     active[(long long)b * T + t] = (power > floor_db || !use_floor) ? 1 : 0;
+    if (est) est[(long long)b * T + t] = 1;
   }
 }
 
@@ -187,7 +190,7 @@ struct mcag_proc_s {
   DevBuf win, tw, spec, chan_pow, chan_raw, power_db, active, gate;
   DevBuf pair_fx, corr, esum, energy, energy_state, raw_idx, raw_prob, cells, prob, cell_state, prob_state;
   DevBuf steer_fx, steer_tab, beams, tail[2], out_dev; int tail_cur = 0;
-  DevBuf lags, curves, curve_state, started;
+  DevBuf lags, curves, curve_state, fg, est, track_doa, track_prob;
   DevBuf mic_fx, srp_ws;
   DevBuf H, H2, thr, stats, gains, Q, noise, dec, qtrace;
   DevBuf band_raw, band_energy, floor_pow, band_cells, mb_raw_cell, mb_raw_prob, mb_lohi;
@@ -248,7 +251,12 @@ static int init_state(mcag_proc p) {
   }
   if (p->energy_state.p) CU(cudaMemsetAsync(p->energy_state.p, 0, p->energy_state.bytes, st));
   if (p->curve_state.p) CU(cudaMemsetAsync(p->curve_state.p, 0, p->curve_state.bytes, st));
-  if (p->started.p) CU(cudaMemsetAsync(p->started.p, 0, p->started.bytes, st));
+  if (p->fg.p) {
+    std::vector<FgState> f((size_t)p->B);
+    for (auto &v : f) { v.alpha = 0.f; v.dalpha = 0.f; v.silence = 0; v.prob = -1.f; v.doa = 0.0; }   // BinauralLocalisation.cpp:323-326,338-339
+    CU(cudaMemcpyAsync(p->fg.p, f.data(), f.size() * sizeof(FgState), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+  }
   if (p->cell_state.p && p->cfg.kind == MCAG_KIND_MULTIBAND) {
     std::vector<int32_t> c((size_t)p->B, -1);              // no cell yet: _currentDOA = 0 rad (MultibandBinarualLocalisation.cpp:78)
     CU(cudaMemcpyAsync(p->cell_state.p, c.data(), c.size() * 4, cudaMemcpyHostToDevice, st));
@@ -275,7 +283,7 @@ void mcag_config_init(mcag_config *c) {
   std::memset(c, 0, sizeof(*c));
   c->frame_size = 512; c->hop = 256; c->n_channels = 2; c->n_streams = 1; c->max_frames_per_call = 256;
   c->n_sources = 1; c->energy_memory = 0.8f; c->corr_memory = 0.8f; c->noise_margin_db = 3.0f; c->floor_seconds = 3.0f;
-  c->mask_method = 1; c->n_bands = 45;
+  c->mask_method = 1; c->n_bands = 45; c->doa_memory = 0.6f;
 }
 
 int mcag_create(const mcag_config *cfg, mcag_proc *out) {
@@ -304,6 +312,8 @@ int mcag_create(const mcag_config *cfg, mcag_proc *out) {
   if (kind == MCAG_KIND_MASK) { p->Cs = 2; p->Cout = 2; }
   int rc = MCAG_OK;
   auto fail = [&](int code) { mcag_destroy(p); return code; };
+  // CUDA failures after this point must release the handle (streams, events, every buffer allocated so far): never the bare CU()
+#define CUF(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(mcag_set_cuda_error(e__)); } while (0)
   if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(mcag_set_error(MCAG_ERR_CUDA, "stream creation failed"));
   if (cudaStreamCreateWithFlags(&p->copy_in, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&p->copy_out, cudaStreamNonBlocking) != cudaSuccess)
     return fail(mcag_set_error(MCAG_ERR_CUDA, "stream creation failed"));
@@ -317,7 +327,7 @@ int mcag_create(const mcag_config *cfg, mcag_proc *out) {
   p->h_window.resize(N);
   for (int n = 0; n < N; ++n) p->h_window[n] = cfg->window ? cfg->window[n] : std::sqrt(0.5 * (1.0 - std::cos(2.0 * M_PI * n / N)));
   { std::vector<float> w(N); for (int n = 0; n < N; ++n) w[n] = (float)p->h_window[n];
-    if ((rc = upload(p->win, w.data(), N * sizeof(float), st))) return fail(rc); CU(cudaStreamSynchronize(st)); }
+    if ((rc = upload(p->win, w.data(), N * sizeof(float), st))) return fail(rc); CUF(cudaStreamSynchronize(st)); }
   if ((rc = p->tw.alloc(sizeof(float2) * fft_table_len(N)))) return fail(rc);
   if ((rc = mcag_k_twiddles(N, p->tw.p, st))) return fail(rc);
 
@@ -379,9 +389,11 @@ int mcag_create(const mcag_config *cfg, mcag_proc *out) {
     if ((rc = k_steer_table(p->steer_fx.as<uint64_t>(), (int)((D + 1) * M), N, p->steer_tab.as<float2>(), st))) return fail(rc);
   }
   if (kind == MCAG_KIND_FREQGCC) {
-    if ((rc = p->curves.alloc(sizeof(float) * B * T * D)) || (rc = p->curve_state.alloc(sizeof(float) * B * D)) || (rc = p->started.alloc(B)) ||
-        (rc = p->cells.alloc(4 * B * T)))
+    if ((rc = p->curves.alloc(sizeof(float) * B * T * D)) || (rc = p->curve_state.alloc(sizeof(float) * B * D)) || (rc = p->fg.alloc(sizeof(FgState) * B)) ||
+        (rc = p->est.alloc(B * T)) || (rc = p->cells.alloc(4 * B * T)))
       return fail(rc);
+    if (cfg->doa_tracker)
+      if ((rc = p->track_doa.alloc(sizeof(double) * B * T)) || (rc = p->track_prob.alloc(sizeof(float) * B * T))) return fail(rc);
   }
   if (kind == MCAG_KIND_MULTIBAND) {
     const size_t nb = cfg->n_bands;
@@ -408,7 +420,7 @@ int mcag_create(const mcag_config *cfg, mcag_proc *out) {
     if ((rc = upload(p->mb_lohi, lohi.data(), lohi.size() * sizeof(int), st))) return fail(rc);
     // MCAG_MB_GENERAL=1 keeps the general three-kernel path (tests compare the two)
     p->mb_fused = p->mb_kmax > p->mb_kmin && k_mb_fused_supported((int)D, p->mb_bw, p->mb_kmin, p->mb_kmax, (int)nb) && !getenv("MCAG_MB_GENERAL");
-    CU(cudaStreamSynchronize(st));
+    CUF(cudaStreamSynchronize(st));
     if ((rc = p->band_raw.alloc(p->mb_fused ? 16 : 4 * B * T * nb * D)) || (rc = p->curves.alloc(4 * B * T * nb * D)) || (rc = p->curve_state.alloc(4 * B * nb * D)) ||
         (rc = p->band_energy.alloc(4 * B * T * nb)) || (rc = p->floor_pow.alloc(4 * B * T)) || (rc = p->energy.alloc(4 * B * T * D)) ||
         (rc = p->band_cells.alloc(4 * B * T * nb)) || (rc = p->mb_raw_cell.alloc(4 * B * T)) || (rc = p->mb_raw_prob.alloc(4 * B * T)) ||
@@ -448,7 +460,7 @@ int mcag_create(const mcag_config *cfg, mcag_proc *out) {
     }
     if ((rc = upload(p->H, H.data(), H.size() * 4, st)) || (rc = upload(p->H2, H2.data(), H2.size() * 4, st)) || (rc = upload(p->thr, thr.data(), nb * 4, st)))
       return fail(rc);
-    CU(cudaStreamSynchronize(st));
+    CUF(cudaStreamSynchronize(st));
     if ((rc = p->stats.alloc(4 * B * T * nb * 6)) || (rc = p->gains.alloc(4 * B * T * nb * 2)) || (rc = p->Q.alloc(4 * B * nb)) ||
         (rc = p->noise.alloc(4 * B * nb)) || (rc = p->dec.alloc(B * T * nb)) || (rc = p->qtrace.alloc(4 * B * T * nb)))
       return fail(rc);
@@ -456,6 +468,7 @@ int mcag_create(const mcag_config *cfg, mcag_proc *out) {
   if ((rc = init_state(p))) return fail(rc);
   *out = p;
   return MCAG_OK;
+#undef CUF
 }
 
 void mcag_destroy(mcag_proc p) {
@@ -467,7 +480,7 @@ void mcag_destroy(mcag_proc p) {
   DevBuf *all[] = {&p->fifo[0], &p->fifo[1], &p->stage_in, &p->stage_out, &p->win, &p->tw, &p->spec, &p->chan_pow, &p->chan_raw, &p->power_db,
                    &p->active, &p->gate, &p->pair_fx, &p->corr, &p->esum, &p->energy, &p->energy_state, &p->raw_idx, &p->raw_prob, &p->cells,
                    &p->prob, &p->cell_state, &p->prob_state, &p->steer_fx, &p->steer_tab, &p->beams, &p->tail[0], &p->tail[1], &p->out_dev,
-                   &p->lags, &p->curves, &p->curve_state, &p->started, &p->mic_fx, &p->srp_ws, &p->H, &p->H2, &p->thr, &p->stats, &p->gains, &p->Q,
+                   &p->lags, &p->curves, &p->curve_state, &p->fg, &p->est, &p->track_doa, &p->track_prob, &p->mic_fx, &p->srp_ws, &p->H, &p->H2, &p->thr, &p->stats, &p->gains, &p->Q,
                    &p->noise, &p->dec, &p->qtrace, &p->band_raw, &p->band_energy, &p->floor_pow, &p->band_cells, &p->mb_raw_cell, &p->mb_raw_prob, &p->mb_lohi};
   for (DevBuf *b : all) b->release();
   for (auto &r : p->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -599,7 +612,8 @@ static int run_frames(mcag_proc p, const float *x_all, long long pitch, int T, i
     PROF(MCAG_PROF_GATE);
     const int needed = (int)(p->cfg.floor_seconds * (float)p->cfg.sample_rate);
     gate_kernel<<<B, 256, 0, st>>>(chan_pow, chan_raw, B, T, M, N, p->cfg.use_power_floor, p->cfg.floor_ccs_power, p->cfg.noise_margin_db, needed,
-                                   p->gate.as<GateState>() + o, p->power_db.as<float>() + o * T, active);
+                                   p->gate.as<GateState>() + o, p->power_db.as<float>() + o * T, active,
+                                   p->est.p ? p->est.as<unsigned char>() + o * T : nullptr);
     MCAG_CHECK_LAUNCH();
     p->launches++;
   }
@@ -675,8 +689,13 @@ static int run_frames(mcag_proc p, const float *x_all, long long pitch, int T, i
     }
     {
       PROF(MCAG_PROF_CURVE_SCAN);
-      OK(k_curve_scan_argmax(corr, B, T, D, 1.0f, p->cfg.corr_memory, active, p->curve_state.as<float>() + o * D,
-                             p->started.as<unsigned char>() + o, p->curves.as<float>() + o * T * D, p->cells.as<int32_t>() + o * T, st));
+      // windowsToDecay = secondsToDecay * fs / (analysisLength/2 - 1) with secondsToDecay = 3 (BinauralLocalisation.cpp:532-533)
+      const int wtd = 3 * p->cfg.sample_rate / (N / 2);
+      const float step = (float)(3 * M_PI / 180);   // _doaStep (:328); the tracker only exists on the reference's 61-cell grid
+      OK(k_curve_scan_argmax(corr, B, T, D, p->cfg.corr_memory, p->cfg.doa_memory, wtd, step, p->track_doa.p != nullptr, active,
+                             p->est.as<unsigned char>() + o * T, p->curve_state.as<float>() + o * D, p->fg.as<FgState>() + o,
+                             p->curves.as<float>() + o * T * D, p->cells.as<int32_t>() + o * T,
+                             p->track_doa.p ? p->track_doa.as<double>() + o * T : nullptr, p->track_prob.p ? p->track_prob.as<float>() + o * T : nullptr, st));
       p->launches += 3;
     }
   } else if (kind == MCAG_KIND_MULTIBAND) {
@@ -861,6 +880,10 @@ static int process_host(mcag_proc p, const Tio *const *in, const Tio *in_packed,
   if (!is_f32 && nsamples > 0 && p->stage_in.bytes < in_bytes) OK(p->stage_in.alloc(in_bytes));
   if (want_audio && !is_f32 && nout > 0) OK(ensure_pinned(&p->pin_out, &p->pin_out_bytes, (size_t)B * Cs * nout * 4));
 
+  // The FIFO may still be read or carried by work a previous mcag_process_device_f32 call left in flight on the compute stream:
+  // the copy-in stream starts behind it.
+  CU(cudaEventRecord(p->ev_done[0], st));
+  CU(cudaStreamWaitEvent(sin, p->ev_done[0], 0));
   // ---- host -> device, one group of streams after the other on the copy-in stream
   for (int c = 0; c < nch && nsamples > 0; ++c) {
     const int r0 = (int)((long long)B * c / nch) * M, r1 = (int)((long long)B * (c + 1) / nch) * M;
@@ -988,7 +1011,8 @@ static const DevBuf *result_buf(mcag_proc p, int what) {
     case MCAG_OUT_CORR: return &p->corr;
     case MCAG_OUT_ENERGY: return &p->energy;
     case MCAG_OUT_CELL: return &p->cells;
-    case MCAG_OUT_PROB: return &p->prob;
+    case MCAG_OUT_PROB: return p->cfg.kind == MCAG_KIND_FREQGCC ? &p->track_prob : &p->prob;
+    case MCAG_OUT_TRACK_DOA: return &p->track_doa;
     case MCAG_OUT_LAGS: return &p->lags;
     case MCAG_OUT_CURVES: return &p->curves;
     case MCAG_OUT_ACTIVE: return &p->active;

@@ -68,40 +68,106 @@ __global__ void select_doa_kernel(const float *__restrict__ energy, long long BT
     float bv = -3.0e38f; int bi = 0x7fffffff;
     for (int i = lane; i < ns; i += 32) { float v = s[i]; if (v > bv) { bv = v; bi = i; } }
     warp_argmax(bv, bi);
+    if (bi >= ns) { bi = 0; bv = s[0]; }   // every candidate NaN (a non-finite input sample): index 0 like wipp::maxidx, never out of bounds
     if (lane == 0) { s[bi] = 0.f; idx[bt * S + r] = bi + 1; prob[bt * S + r] = bv; }
     __syncwarp();
   }
 }
 
-// FreqGCC smoothing: c_t = (1-alpha) corr_t + alpha c_{t-1}, alpha = 0 up to and including the first active frame,
-// `mem` afterwards (BinauralLocalisation.cpp:444-448,523); one thread per (stream, delay).
-__global__ void curve_scan_kernel(const float *__restrict__ corr, int B, int T, int D, float mem, const unsigned char *__restrict__ active,
-                                  float *__restrict__ state, const unsigned char *__restrict__ started_in, float *__restrict__ curves) {
+// FreqGCC smoothing: c_t = (1-alpha) corr_t + alpha c_{t-1} on frames the gate lets through (BinauralLocalisation.cpp:444-448).  alpha is
+// the reference's _corrMemoryFactor state machine (:323,523,528-561): 0 at construction, `mem` after every voiced frame; on a gated
+// frame with the noise floor estimated it is `mem` while fewer than windowsToDecay = 3 fs/(N/2) silent frames have passed and 0
+// afterwards (so the first voiced frame after a long pause REPLACES the curve), and the silent-frame counter advances.  One thread per
+// (stream, delay); every thread of a stream replays the same (alpha, silence) sequence from the carried FgState, fg_track_kernel
+// writes the state back.  `est` [B][T]: noise floor estimated when the frame was gated (gate_kernel); NULL = always.
+__global__ void curve_scan_kernel(const float *__restrict__ corr, int B, int T, int D, float mem, int windows_to_decay,
+                                  const unsigned char *__restrict__ active, const unsigned char *__restrict__ est, float *__restrict__ state,
+                                  const FgState *__restrict__ fg, float *__restrict__ curves) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * D) return;
   const int b = i / D, d = i - b * D;
   float prev = state[i];
-  bool started = started_in[b] != 0;
-  // only `prev` and `started` are carried: the loads are unconditional and the loop is unrolled so that eight frames of inputs are in
-  // flight per thread (one frame at a time the kernel was bound by the latency of its dependent loads)
+  float alpha = fg[b].alpha;
+  int silence = fg[b].silence;
+  // the loads are unconditional and the loop is unrolled so that eight frames of inputs are in flight per thread (one frame at a
+  // time the kernel was bound by the latency of its dependent loads)
 #pragma unroll 8
   for (int t = 0; t < T; ++t) {
     const long long o = ((long long)b * T + t) * D + d;
     const float c = corr[o];
     const bool on = !active || active[(long long)b * T + t];
+    const bool e = !est || est[(long long)b * T + t];
     if (on) {
-      const float alpha = started ? mem : 0.f;
       prev = (1.f - alpha) * c + alpha * prev;
-      started = true;
+      alpha = mem; silence = 0;
+    } else if (e) {
+      alpha = silence < windows_to_decay ? mem : 0.f;
+      ++silence;
     }
     curves[o] = prev;
   }
   state[i] = prev;
 }
-__global__ void started_update_kernel(int B, int T, const unsigned char *__restrict__ active, unsigned char *__restrict__ started) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B || started[b]) return;
-  for (int t = 0; t < T; ++t) if (!active || active[(long long)b * T + t]) { started[b] = 1; return; }
+
+// Per-stream state of FreqGCCBinauralLocalisation after the frames of a call: the memory-factor state machine above, plus (track != 0)
+// the deterministic DOA tracker = the `#else` branch of USE_PARTICLE_FILTER (BinauralLocalisation.cpp:501-504):
+//   setProbability(_currentDOA, _prob, 1) on this frame's smoothed curve with the PREVIOUS _currentDOA (:454,569-631),
+//   _currentDOA = _doaMemoryFactor * _currentDOA + (1 - _doaMemoryFactor) * doaIdx2angle(argmax)  (float factor, double DOA),
+//   _doaMemoryFactor: 0 -> dmem (0.6f) after a voiced frame (:524), 0 again after windowsToDecay silent frames (:555).
+// One warp per stream, frames in order; lanes share the 61-cell min / sum reductions, lane 0 carries the doubles.
+__global__ void __launch_bounds__(128) fg_track_kernel(const float *__restrict__ curves, const int32_t *__restrict__ idx, int B, int T, int D, float mem,
+                                                      float dmem, int windows_to_decay, float doa_step, int track,
+                                                      const unsigned char *__restrict__ active, const unsigned char *__restrict__ est,
+                                                      FgState *__restrict__ fg, double *__restrict__ track_doa, float *__restrict__ track_prob) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  FgState s = fg[b];
+  auto cell_angle = [&](int i) { return (double)(float)((double)((float)i * doa_step) - 1.57079632679489661923); };   // doaIdx2angle (float-typed)
+  for (int t = 0; t < T; ++t) {
+    const long long bt = (long long)b * T + t;
+    const bool on = !active || active[bt];
+    const bool e = !est || est[bt];
+    if (on) {
+      if (track) {
+        const float *c = curves + bt * D;
+        float mn = 3.0e38f; double sm = 0.0;
+        for (int i = lane; i < D; i += 32) { const float v = c[i]; mn = fminf(mn, v); sm += (double)v; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); sm += __shfl_xor_sync(0xffffffffu, sm, o); }
+        if (lane == 0) {
+          sm = __dsub_rn(sm, __dmul_rn((double)mn, (double)D));
+          // angle2DOAidx (microhponeArrayHelpers.cpp:110-115) of the previous DOA, as a float
+          float ang = (float)s.doa;
+          ang = (float)fmax((double)ang, -1.57079632679489661923);
+          ang = (float)fmin((double)ang, 1.57079632679489661923);
+          const int ci = (int)(((double)ang + 1.57079632679489661923) / (double)doa_step);
+          const double angle = cell_angle(ci);
+          double p;
+          if (0 < ci && ci < D - 1) {
+            double pc, pd, nc, nd;
+            if (angle > s.doa) { pc = c[ci - 1]; pd = cell_angle(ci - 1); nc = c[ci]; nd = angle; }
+            else { pc = c[ci]; pd = angle; nc = c[ci + 1]; nd = cell_angle(ci + 1); }
+            const double slope = __ddiv_rn(__dsub_rn(nc, pc), __dsub_rn(nd, pd));
+            p = __dadd_rn(__dmul_rn(slope, __dsub_rn(s.doa, pd)), pc);
+          } else {
+            p = c[min(max(ci, 0), D - 1)];
+          }
+          double pr = 0.0;
+          if (sm > 0.0) pr = __ddiv_rn(__dsub_rn(p, (double)mn), sm);
+          s.prob = (pr < 0.01) ? 0.f : (float)pr;
+          const double doa = cell_angle(idx[bt]);
+          s.doa = __dadd_rn(__dmul_rn((double)s.dalpha, s.doa), __dmul_rn((double)(1.f - s.dalpha), doa));
+        }
+      }
+      s.alpha = mem; s.dalpha = dmem; s.silence = 0;
+    } else if (e) {
+      const bool decay = s.silence < windows_to_decay;
+      s.alpha = decay ? mem : 0.f; s.dalpha = decay ? dmem : 0.f;
+      ++s.silence;
+    }
+    if (track && lane == 0) { track_doa[bt] = s.doa; track_prob[bt] = s.prob; }
+  }
+  if (lane == 0) fg[b] = s;
 }
 __global__ void row_argmax_kernel(const float *__restrict__ x, long long rows, int D, int32_t *__restrict__ idx) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -110,6 +176,7 @@ __global__ void row_argmax_kernel(const float *__restrict__ x, long long rows, i
   float bv = -3.0e38f; int bi = 0x7fffffff;
   for (int i = lane; i < D; i += 32) { float v = x[row * D + i]; if (v > bv) { bv = v; bi = i; } }
   warp_argmax(bv, bi);
+  if (bi >= D) bi = 0;   // all-NaN row: index 0 like wipp::maxidx
   if (lane == 0) idx[row] = bi;
 }
 
@@ -123,6 +190,7 @@ __global__ void argmax_pack_kernel(const float *__restrict__ x, long long rows, 
   float bv = -3.0e38f; int bi = 0x7fffffff;
   for (int i = lane; i < D; i += 32) { float v = x[row * D + i]; if (v > bv) { bv = v; bi = i; } }
   warp_argmax(bv, bi);
+  if (bi >= D) bi = 0;   // all-NaN row: index 0 like wipp::maxidx
   if (lane == 0) {
     uint32_t u = __float_as_uint(bv);
     u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -161,15 +229,16 @@ int k_select_doa(const float *energy, long long BT, int D, int n_pairs, int S, i
   MCAG_CHECK_LAUNCH();
   return 0;
 }
-int k_curve_scan_argmax(const float *corr, int B, int T, int D, float, float mem, const unsigned char *active, float *state,
-                        unsigned char *started, float *curves, int32_t *idx, cudaStream_t st) {
+int k_curve_scan_argmax(const float *corr, int B, int T, int D, float mem, float dmem, int windows_to_decay, float doa_step, int track,
+                        const unsigned char *active, const unsigned char *est, float *state, FgState *fg, float *curves, int32_t *idx,
+                        double *track_doa, float *track_prob, cudaStream_t st) {
   if (B * D <= 0 || T <= 0) return 0;
-  curve_scan_kernel<<<(B * D + 127) / 128, 128, 0, st>>>(corr, B, T, D, mem, active, state, started, curves);
-  MCAG_CHECK_LAUNCH();
-  started_update_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, T, active, started);
+  curve_scan_kernel<<<(B * D + 127) / 128, 128, 0, st>>>(corr, B, T, D, mem, windows_to_decay, active, est, state, fg, curves);
   MCAG_CHECK_LAUNCH();
   const long long rows = (long long)B * T;
   row_argmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(curves, rows, D, idx);
+  MCAG_CHECK_LAUNCH();
+  fg_track_kernel<<<(B + 3) / 4, 128, 0, st>>>(curves, idx, B, T, D, mem, dmem, windows_to_decay, doa_step, track, active, est, fg, track_doa, track_prob);
   MCAG_CHECK_LAUNCH();
   return 0;
 }

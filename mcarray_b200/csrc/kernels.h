@@ -24,8 +24,12 @@ int k_pair_sum(const float *corr, long long BT, int P, int D, float scale, float
 int k_energy_scan(const float *esum, int B, int T, int D, float a, const unsigned char *active, float *state, float *energy, cudaStream_t st);
 int k_argmax_pack(const float *x, long long rows, int D, int d_offset, long long *packed, cudaStream_t st);
 int k_select_doa(const float *energy, long long BT, int D, int n_pairs, int S, int32_t *idx, float *prob, cudaStream_t st);
-int k_curve_scan_argmax(const float *corr, int B, int T, int D, float keep_first, float mem, const unsigned char *active, float *state,
-                        unsigned char *started, float *curves, int32_t *idx, cudaStream_t st);
+// FreqGCCBinauralLocalisation per-stream state carried across calls (BinauralLocalisation.h:200-213)
+struct FgState { float alpha /* _corrMemoryFactor */, dalpha /* _doaMemoryFactor */; int silence /* _silenceFramesCounter */; float prob /* _prob[0] */;
+                 double doa /* _currentDOA[0], rad */; };
+int k_curve_scan_argmax(const float *corr, int B, int T, int D, float mem, float dmem, int windows_to_decay, float doa_step, int track,
+                        const unsigned char *active, const unsigned char *est, float *state, FgState *fg, float *curves, int32_t *idx,
+                        double *track_doa, float *track_prob, cudaStream_t st);
 
 // beamform.cu
 int k_steer_table(const uint64_t *fx, int DM, int N, float2 *tab, cudaStream_t st);

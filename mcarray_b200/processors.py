@@ -20,7 +20,7 @@ MaskingAlg = dict(BOTH=0, SPATIAL=1, TEMPORAL=2)                          # Arra
 _OUT_DTYPE = {capi.OUT_SPECTRA: np.complex64, capi.OUT_POWER_DB: np.float32, capi.OUT_CORR: np.float32, capi.OUT_ENERGY: np.float32,
               capi.OUT_CELL: np.int32, capi.OUT_PROB: np.float32, capi.OUT_LAGS: np.int32, capi.OUT_CURVES: np.float32,
               capi.OUT_ACTIVE: np.uint8, capi.OUT_BEAMS: np.complex64, capi.OUT_MASK_Q: np.float32, capi.OUT_MASK_DEC: np.uint8,
-              capi.OUT_BAND_CELL: np.int32}
+              capi.OUT_BAND_CELL: np.int32, capi.OUT_TRACK_DOA: np.float64}
 
 
 _default_device = 0
@@ -199,14 +199,21 @@ class SourceLocalisation(_Localiser):
 
 class FreqGCCBinauralLocalisation(Processor):
     def __init__(self, sampleRate, microphoneDistance, usePowerFloor=True, n_streams=1, max_frames_per_call=256, frame_size=None,
-                 noise_preestimated=True):
+                 noise_preestimated=True, deterministic_tracker=False):
         self.doa_step = np.float32(3 * np.pi / 180)                         # BinauralLocalisation.cpp:328
         N = frame_size or capi.frame_size(sampleRate, 0.075)                # BinauralLocalisation.h:196
         xyz = np.array([[0.0, 0, 0], [microphoneDistance, 0, 0]])
         tau = capi.pair_tau_reference(xyz, sampleRate, self.doa_step)       # same helper chain as :363-366
         super().__init__(kind=capi.KIND_FREQGCC, sample_rate=sampleRate, frame_size=N, hop=N // 2, n_channels=2, n_streams=n_streams,
                          max_frames_per_call=max_frames_per_call, n_dirs=tau.shape[1], pair_tau=tau, use_power_floor=int(usePowerFloor),
-                         noise_margin_db=6.0, floor_ccs_power=1, noise_preestimated=int(noise_preestimated), corr_memory=0.8)
+                         noise_margin_db=6.0, floor_ccs_power=1, noise_preestimated=int(noise_preestimated), corr_memory=0.8,
+                         doa_tracker=int(deterministic_tracker), doa_memory=0.6)   # _maxDoaMemoryFactor, BinauralLocalisation.h:199
+        self._tracker = bool(deterministic_tracker)
+        self._callback = None
+
+    def setCallback(self, cb):
+        """cb(doa_deg [1], prob [1], power, 1) — BinauralLocalisation.cpp:521"""
+        self._callback = cb
 
     def curves(self):
         B, T = self._bt()
@@ -214,6 +221,30 @@ class FreqGCCBinauralLocalisation(Processor):
 
     def cells(self):
         return self.fetch(capi.OUT_CELL, self._bt())
+
+    def tracked_doa(self):
+        """deterministic_tracker: _currentDOA (rad) after every frame, the `#else` branch of BinauralLocalisation.cpp:501-504"""
+        return self.fetch(capi.OUT_TRACK_DOA, self._bt())
+
+    def prob(self):
+        """deterministic_tracker: setProbability (BinauralLocalisation.cpp:454,569-631) after every frame"""
+        return self.fetch(capi.OUT_PROB, self._bt())
+
+    def process(self, x):
+        y = super().process(x)
+        if self._callback is not None and self.frames_done:
+            act, power = self.active(), self.power_db()
+            if self._tracker:
+                doa, prob = np.degrees(self.tracked_doa()), self.prob()
+            else:
+                cells = self.cells()
+                ang = np.array([capi.cell_angle(i, self.doa_step) for i in range(self.info.n_dirs)])
+                doa, prob = np.degrees(ang[cells]), np.ones(cells.shape)
+            for b in range(self.info.n_streams):
+                for t in range(self.frames_done):
+                    if act[b, t]:
+                        self._callback(doa[b, t:t + 1], prob[b, t:t + 1], float(power[b, t]), 1)
+        return y
 
 
 class MultibandBinarualLocalisation(Processor):

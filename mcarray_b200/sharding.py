@@ -88,7 +88,7 @@ class ShardedSrpPhat:
                                                   capi.vp(packed), C.c_void_p(lib.mcag_stream(p.handle))))
                 allreduce_argmax(packed, self.group)
             val, idx = unpack_max(packed)
-        return val.view(p.info.n_streams, -1), idx.view(p.info.n_streams, -1)
+        return val.view(p.info.n_streams, p.frames_done), idx.view(p.info.n_streams, p.frames_done)   # explicit shape: a call may complete 0 frames
 
     def process(self, x):
         """x [B*M][n] host array (identical on every rank) -> (peak energy [B][T], global direction cell [B][T]) on every rank."""

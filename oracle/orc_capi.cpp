@@ -167,6 +167,39 @@ extern "C" int orc_multiband_frames(const double *spec, int T, int N, int fs, do
   return st.D;
 }
 
+// FreqGCC with the deterministic DOA tracker (the `#else` branch of USE_PARTICLE_FILTER, BinauralLocalisation.cpp:501-504) and
+// setProbability (:454,569-631): per frame t (every frame, fired or not) active[t], doa_rad[t] = _currentDOA, prob[t] = _prob,
+// idx[t] / curves[t][61] valid on active frames (previous values are held otherwise).
+namespace {
+struct GccTrack { FreqGccState st; int frame = 0, max_frames = 0; int *active, *idx; double *doa, *prob, *curves, *power; int last_idx = 0; };
+void gcc_track_hook(void *user, double *frames, int, int) {
+  GccTrack &r = *static_cast<GccTrack *>(user);
+  std::vector<double> curve(static_cast<size_t>(r.st.D)); int idx = r.last_idx;
+  FrameReport rep = freqgcc_frame(r.st, frames, curve.data(), &idx);
+  if (r.frame < r.max_frames) {
+    const int t = r.frame;
+    r.active[t] = rep.fired ? 1 : 0; r.doa[t] = r.st.cur_doa; r.prob[t] = r.st.prob; r.power[t] = rep.power;
+    if (rep.fired) { r.last_idx = idx; std::copy(curve.begin(), curve.end(), r.curves + size_t(t) * r.st.D); }
+    else std::copy(r.st.prev_corr.begin(), r.st.prev_corr.end(), r.curves + size_t(t) * r.st.D);
+    r.idx[t] = r.last_idx;
+  }
+  ++r.frame;
+}
+}  // namespace
+extern "C" int orc_freqgcc_track_run(int fs, double mic_dist, int N, int use_floor, int noise_preestimated, const double *in, int n, int chunk,
+                                     int max_frames, int *n_frames, int *active, double *doa_rad, double *prob, int *idx, double *curves, double *power) {
+  int order = 0;
+  if (N > 0) { while ((1 << order) < N) ++order; } else order = dsp::ShortTimeProcess::calculateOrderFromSampleRate(fs, 0.075f);
+  GccTrack r;
+  r.st.init(fs, mic_dist, 1 << order, use_floor != 0);
+  if (noise_preestimated) r.st.noise_estimated = true;
+  r.max_frames = max_frames; r.active = active; r.doa = doa_rad; r.prob = prob; r.idx = idx; r.curves = curves; r.power = power;
+  FrameTap tap(2, order, false, gcc_track_hook, &r);
+  feed(tap, 2, in, n, chunk, nullptr, 0, false);
+  if (n_frames) *n_frames = r.frame;
+  return 1 << order;
+}
+
 void orc_freqgcc_probability(int, double, const double *curve, const double *doas, double *probs, int size) {
   const float step = float(3 * M_PI / 180);
   freqgcc_probability(curve, num_doa_steps(step), step, doas, probs, size);

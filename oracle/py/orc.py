@@ -121,6 +121,23 @@ def freqgcc_run(fs, mic_dist, x, chunk=0, use_floor=False, noise_preestimated=Tr
                 idx=idx[:f].copy(), power=power[:f].copy())
 
 
+def freqgcc_track_run(fs, mic_dist, x, chunk=0, use_floor=True, noise_preestimated=False, N=0):
+    """FreqGCC with the deterministic tracker (the `#else` branch, BinauralLocalisation.cpp:501-504): per-frame arrays for EVERY frame."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n = x.shape[1]
+    Nn = N or frame_size(fs, np.float32(0.075))
+    maxf = max(1, n // (Nn // 2) + 2)
+    n_frames = C.c_int(0)
+    active = np.zeros(maxf, dtype=np.int32); idx = np.zeros(maxf, dtype=np.int32)
+    doa = np.zeros(maxf); prob = np.zeros(maxf); power = np.zeros(maxf); curves = np.zeros((maxf, 61))
+    r = lib("orc").orc_freqgcc_track_run(C.c_int(fs), C.c_double(mic_dist), C.c_int(N), C.c_int(int(use_floor)), C.c_int(int(noise_preestimated)),
+                                        _dp(x), C.c_int(n), C.c_int(chunk), C.c_int(maxf), C.byref(n_frames), _ip(active), _dp(doa), _dp(prob),
+                                        _ip(idx), _dp(curves), _dp(power))
+    f = n_frames.value
+    return dict(N=r, n_frames=f, active=active[:f].copy(), doa_rad=doa[:f].copy(), prob=prob[:f].copy(), idx=idx[:f].copy(),
+                curves=curves[:f].copy(), power=power[:f].copy())
+
+
 def multiband_run(fs, mic_dist, x, nbins=15, chunk=0, use_floor=False, noise_preestimated=True, prefix="orc"):
     """MultibandBinarualLocalisation (MultibandBinarualLocalisation.cpp:52-259) over a whole stereo signal."""
     x = np.ascontiguousarray(x, dtype=np.float64)

@@ -257,6 +257,8 @@ struct FreqGccState {
   double mic_dist;
   std::vector<double> tau, prev_corr;
   float corr_mem;                         // 0 until the first voiced frame, then 0.8f (:323,523)
+  float doa_mem;                          // _doaMemoryFactor: 0 (:324) -> _maxDoaMemoryFactor = 0.6f (.h:199) after a voiced frame (:524)
+  double cur_doa, prob;                   // _currentDOA[0] = 0, _prob[0] = -1 (:338-339); deterministic tracker = the #else branch (:501-504)
   double power_floor; bool noise_estimated; int samples_for_noise; int silence_frames;
   void init(int fs_, double mic_dist_, int N, bool use_floor_) {
     fs = fs_; K = N / 2 + 1; use_floor = use_floor_; mic_dist = mic_dist_;
@@ -264,10 +266,12 @@ struct FreqGccState {
     D = num_doa_steps(doa_step);                                                           // :329
     tau.resize(size_t(D));
     for (int i = 0; i < D; ++i) tau[size_t(i)] = doa_to_delay_far_field_samples(doa_idx_to_angle(i, doa_step), float(mic_dist), fs);  // :363-366
-    prev_corr.assign(size_t(D), 0.0); corr_mem = 0;
+    prev_corr.assign(size_t(D), 0.0); corr_mem = 0; doa_mem = 0; cur_doa = 0; prob = -1;
     power_floor = 0; noise_estimated = false; samples_for_noise = 0; silence_frames = 0;
   }
 };
+
+inline void freqgcc_probability(const double *curve, int D, float doa_step, const double *doas, double *probs, int size);
 
 // frames [2][N+2]; curve_out [D] = smoothed correlation; returns fired flag; *idx_out = argmax cell.
 inline FrameReport freqgcc_frame(FreqGccState &st, const double *frames, double *curve_out, int *idx_out) {
@@ -299,17 +303,22 @@ inline FrameReport freqgcc_frame(FreqGccState &st, const double *frames, double 
       c[size_t(d)] += st.prev_corr[size_t(d)];
       st.prev_corr[size_t(d)] = c[size_t(d)];
     }
+    freqgcc_probability(c.data(), st.D, st.doa_step, &st.cur_doa, &st.prob, 1);            // :454, with the PREVIOUS _currentDOA
     double mx; size_t mi;
     wipp::maxidx(c.data(), size_t(st.D), &mx, &mi);                                        // :459 / :502
+    // deterministic tracker: the `#else` branch of USE_PARTICLE_FILTER (:501-504).  float * double and (1 - float) as written there.
+    const double doa = doa_idx_to_angle(int(mi), st.doa_step);
+    st.cur_doa = st.doa_mem * st.cur_doa + (1 - st.doa_mem) * doa;
     if (curve_out) std::copy(c.begin(), c.end(), curve_out);
     if (idx_out) *idx_out = int(mi);
     st.corr_mem = 0.8f;                                                                    // :523
+    st.doa_mem = 0.6f;                                                                     // :524
     st.silence_frames = 0;
     r.fired = true;
   } else if (st.noise_estimated) {                                                         // :528-561
     const int windows_to_decay = 3 * st.fs / (ccs / 2 - 1);
-    if (st.silence_frames < windows_to_decay) st.corr_mem = 0.8f;
-    else st.corr_mem = 0;
+    if (st.silence_frames < windows_to_decay) { st.corr_mem = 0.8f; st.doa_mem = 0.6f; }
+    else { st.corr_mem = 0; st.doa_mem = 0; }
     ++st.silence_frames;
   }
   return r;

@@ -15,6 +15,20 @@ from mcarray_b200 import scenes  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+def pause_scene(fs=16000, hop=1024):
+    """voiced(-21 deg) 8 frames | quiet 10 | voiced(+33) 10 | quiet 52 | voiced(-48) 10 | quiet 3; int16 PCM (the pauses are sparse +-1 LSB
+    dither, about -13 dB against the forced 0 dB floor)"""
+    xyz = scenes.linear_array([0, 0.086])
+
+    def voiced(nf, az, seed):
+        return scenes.far_field_scene(xyz, fs, nf * hop, scenes.azimuth_dirs([np.deg2rad(az)]), seed=seed)
+
+    def quiet(nf, seed):
+        return np.random.default_rng(seed).choice([-1.0, 0.0, 1.0], size=(2, nf * hop), p=[0.05, 0.9, 0.05])
+    x = np.concatenate([voiced(8, -21, 1), quiet(10, 2), voiced(10, 33, 3), quiet(52, 4), voiced(10, -48, 5), quiet(3, 6)], axis=1)
+    return np.round(x)
+
+
 def main():
     orc.build(ref=True)
     assert orc.have_ref(), "reference build unavailable"
@@ -50,6 +64,17 @@ def main():
     r = orc.freqgcc_run(fs, 0.086, x, chunk=2048, prefix="ref")
     np.savez_compressed(os.path.join(HERE, "freqgcc_16k.npz"), fs=fs, mic_dist=0.086, x=x.astype(np.int16), chunk=2048,
                         curves=r["curves"], idx=r["idx"], power=r["power"], N=r["N"])
+    # 3a. the same processor with usePowerFloor = true and pauses: exercises the _corrMemoryFactor / _silenceFramesCounter state machine
+    #     (BinauralLocalisation.cpp:523-561).  N = 2048, hop = 1024 -> windowsToDecay = 46 frames: the 10-frame pause keeps the 0.8
+    #     memory, the 52-frame pause resets it (the next voiced frame replaces the curve).  _noiseEstimated is forced (floor 0 dB), the
+    #     only way the reference build runs (oracle/capi.h).  The reference's particle filter also fires the callback on silent frames
+    #     inside the decay window (:540-544); those deliveries carry power <= floor and are dropped here.
+    x = pause_scene()
+    r = orc.freqgcc_run(fs, 0.086, x, chunk=2500, use_floor=True, prefix="ref")
+    voiced = r["power"] > 0
+    np.savez_compressed(os.path.join(HERE, "freqgcc_floor_16k.npz"), fs=fs, mic_dist=0.086, x=x.astype(np.int16), chunk=2500,
+                        curves=r["curves"][voiced], idx=r["idx"][voiced], power=r["power"][voiced], fired_frame=r["fired_frame"][voiced],
+                        n_frames=r["n_frames"], N=r["N"])
     # 3b. MultibandBinarualLocalisation, 0.086 m, 15 linear bands; source moves from +35 to -20 degrees half way
     fs = 16000
     xyz = scenes.linear_array([0, 0.086])

@@ -209,6 +209,70 @@ def test_freqgcc_against_reference_golden(mb):
     assert_close(curves, g["curves"], (1,), "smoothed GCC curve")
 
 
+def test_freqgcc_power_floor_against_reference_golden(mb):
+    """usePowerFloor = true with pauses, fixture from the reference build: the device _corrMemoryFactor state machine
+    (BinauralLocalisation.cpp:523-561) must keep the 0.8 memory over the short pause and restart the curve after the >= 3 s one."""
+    g = np.load(os.path.join(G, "freqgcc_floor_16k.npz"))
+    x = g["x"].astype(np.float32)
+    p = mb.FreqGCCBinauralLocalisation(int(g["fs"]), float(g["mic_dist"]), usePowerFloor=True, max_frames_per_call=8, noise_preestimated=True)
+    fired = []
+    p.setCallback(lambda doa, prob, power, n: fired.append(power))
+    curves, idx, act = [], [], []
+    for pos in range(0, x.shape[1], int(g["chunk"])):
+        p.process(x[:, pos:pos + int(g["chunk"])])
+        if p.frames_done:
+            curves.append(p.curves()[0]); idx.append(p.cells()[0]); act.append(p.active()[0])
+    curves = np.concatenate(curves); idx = np.concatenate(idx); act = np.concatenate(act).astype(bool)
+    assert len(act) == int(g["n_frames"])
+    assert np.array_equal(np.nonzero(act)[0], g["fired_frame"])
+    assert np.array_equal(idx[act], g["idx"])
+    assert_close(curves[act], g["curves"], (1,), "smoothed GCC curve, power floor on")
+    assert len(fired) == len(g["fired_frame"]) and np.allclose(fired, g["power"], rtol=0, atol=1e-3)
+
+
+def _floor_scene(fs=16000, hop=256):
+    """quiet lead-in (the 3 s noise estimate + 10 more frames) | voiced 40 | quiet 200 (> windowsToDecay = 187) | voiced 40 | quiet 20 | voiced 30"""
+    xyz = scenes.linear_array([0, 0.086])
+    rng = np.random.default_rng(77)
+
+    def voiced(nf, az, seed):
+        return scenes.far_field_scene(xyz, fs, nf * hop, scenes.azimuth_dirs([np.deg2rad(az)]), seed=seed)
+
+    def quiet(nf):
+        return rng.standard_normal((2, nf * hop)) * 3.0
+    return np.concatenate([quiet(105), voiced(40, 40, 11), quiet(200), voiced(40, -25, 12), quiet(20), voiced(30, 10, 13), quiet(5)], axis=1)
+
+
+@pytest.mark.parametrize("chunk", [0, 3000])
+def test_freqgcc_power_floor_state_machine_vs_oracle(mb, orc, chunk):
+    """FreqGCC with usePowerFloor = true and the floor ESTIMATED on the device (noise_preestimated = False), N = 512: gate flags, arg-max
+    cells and the deterministic tracker's DOA bit-exact against the oracle, curves and setProbability within tolerance; the scene has a
+    pause longer than windowsToDecay (restart with alpha = 0) and a short one (alpha stays 0.8)."""
+    x = _floor_scene()
+    ref = orc.freqgcc_track_run(16000, 0.086, x, chunk=chunk, use_floor=True, noise_preestimated=False, N=512)
+    T = ref["n_frames"]
+    p = mb.FreqGCCBinauralLocalisation(16000, 0.086, usePowerFloor=True, max_frames_per_call=T + 1, frame_size=512, noise_preestimated=False,
+                                       deterministic_tracker=True)
+    step = chunk or x.shape[1]
+    act, idx, curves, doa, prob = [], [], [], [], []
+    for pos in range(0, x.shape[1], step):
+        p.process(x[:, pos:pos + step].astype(np.float32))
+        if p.frames_done:
+            act.append(p.active()[0]); idx.append(p.cells()[0]); curves.append(p.curves()[0]); doa.append(p.tracked_doa()[0]); prob.append(p.prob()[0])
+    act = np.concatenate(act).astype(bool); idx = np.concatenate(idx); curves = np.concatenate(curves); doa = np.concatenate(doa); prob = np.concatenate(prob)
+    assert len(act) == T and 100 < act.sum() < 125
+    assert np.array_equal(act, ref["active"].astype(bool))
+    assert np.array_equal(idx[act], ref["idx"][act])
+    assert_close(curves[act], ref["curves"][act], (1,), "smoothed GCC curve")
+    assert_close(curves[~act], ref["curves"][~act], (1,), "held curve on gated frames")
+    assert np.array_equal(doa, ref["doa_rad"]), np.max(np.abs(doa - ref["doa_rad"]))
+    near_cut = np.abs(ref["prob"] - 0.01) < 1e-4                        # setProbability zeroes values below 0.01 (:628)
+    assert np.allclose(prob[~near_cut], ref["prob"][~near_cut], rtol=1e-3, atol=1e-5)
+    voiced = np.nonzero(act)[0]
+    first_after_long_pause = voiced[np.nonzero(np.diff(voiced) > 187)[0][0] + 1]
+    assert abs(np.degrees(doa[first_after_long_pause]) + 24) <= 1.5      # restarted: no memory of the +40 degree source
+
+
 def test_multiband_against_reference_golden(mb):
     """N2 MultibandBinarualLocalisation against the fixture produced by the reference's own MultibandBinarualLocalisation.cpp:
     published cells and per-band arg-max cells bit-exact, histogram / prob within tolerance, callback deliveries in order."""

@@ -42,6 +42,24 @@ def test_golden_freqgcc(orc):
     assert np.all(g["idx"] == 23)  # -21 degrees on the 3-degree grid
 
 
+def test_golden_freqgcc_power_floor_pauses(orc):
+    """usePowerFloor = true with a short and a long pause (fixture from the reference build): the restated _corrMemoryFactor state machine
+    (BinauralLocalisation.cpp:523-561) keeps the 0.8 memory over the 10-frame pause and restarts the curve after the 52-frame one."""
+    g = np.load(os.path.join(G, "freqgcc_floor_16k.npz"))
+    r = orc.freqgcc_run(int(g["fs"]), float(g["mic_dist"]), g["x"].astype(np.float64), chunk=int(g["chunk"]), use_floor=True)
+    assert r["n_frames"] == int(g["n_frames"])
+    for k in ("fired_frame", "curves", "idx", "power"):
+        assert np.array_equal(r[k], g[k]), k
+    f = list(g["fired_frame"])
+    assert g["idx"][f.index(17)] == 23 and g["idx"][f.index(20)] == 41      # short pause: the old curve still weighs 0.8
+    assert g["idx"][f.index(79)] == 14                                        # long pause: the first voiced frame replaces the curve
+    # the deterministic tracker (the `#else` branch, :501-504) rides on the same frames: DOA memory 0 -> 0.6 -> 0 after the long pause
+    t = orc.freqgcc_track_run(int(g["fs"]), float(g["mic_dist"]), g["x"].astype(np.float64), chunk=int(g["chunk"]), use_floor=True, noise_preestimated=True)
+    assert np.array_equal(np.nonzero(t["active"])[0], g["fired_frame"]) and np.array_equal(t["idx"][t["active"] > 0], g["idx"])
+    deg = np.degrees(t["doa_rad"])
+    assert abs(deg[0] + 21) < 1e-4 and abs(deg[79] + 48) < 1e-4 and -21 < deg[19] < -19 and 30 < deg[27] < 33
+
+
 def test_golden_mask(orc):
     g = np.load(os.path.join(G, "mask_spatial_16k.npz"))
     x = g["x"].astype(np.float64)

@@ -1,6 +1,8 @@
 """Pins the oracle restatement (oracle/restated.hpp) to the REFERENCE'S OWN CODE: oracle/_ref is the
 reference's .cpp files compiled from /root/reference against the DSPONE/WIPP stand-in (oracle/Makefile).
 Everything mcarray owns must agree bit for bit.  Skipped only when no prebuilt oracle/_ref exists."""
+import os
+
 import numpy as np
 import pytest
 
@@ -57,6 +59,21 @@ def test_freqgcc_bit_exact(orc):
     doas = np.linspace(-1.5, 1.5, 41)
     c = a["curves"][5]
     assert np.array_equal(orc.freqgcc_probability(fs, 0.086, c, doas), orc.freqgcc_probability(fs, 0.086, c, doas, prefix="ref"))
+
+
+def test_freqgcc_power_floor_pauses_bit_exact(orc):
+    """the silence branch of BinauralLocalisation.cpp:528-561 against the reference build, on the scene the golden fixture is made from"""
+    sys_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(sys_path, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    x = mg.pause_scene()
+    a = orc.freqgcc_run(16000, 0.086, x, chunk=999, use_floor=True)
+    b = orc.freqgcc_run(16000, 0.086, x, chunk=999, use_floor=True, prefix="ref")
+    voiced = b["power"] > 0          # the particle filter also delivers on silent frames inside the decay window (:540-544)
+    assert a["n_fired"] == voiced.sum() == 30 and b["n_fired"] > a["n_fired"]
+    for k in ("fired_frame", "curves", "idx", "power"):
+        assert np.array_equal(a[k], b[k][voiced]), k
 
 
 @pytest.mark.parametrize("method", [0, 1, 3, 4, 5])
