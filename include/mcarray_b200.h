@@ -155,6 +155,9 @@ int mcag_process_f64(mcag_proc p, const double *const *in, int nsamples, double 
 int mcag_process_s16(mcag_proc p, const int16_t *const *in, int nsamples, int16_t *const *out, int out_capacity, int *nsamples_out);
 /* Same with one contiguous host block per call: in [B*M][in_pitch], out [B*C][out_pitch] (pinned memory recommended). */
 int mcag_process_packed_f32(mcag_proc p, const float *in, long long in_pitch, int nsamples, float *out, long long out_pitch, int *nsamples_out);
+/* ... and with 16-bit PCM, the sample type of the reference's process(std::vector<int16_t*>&, ...) overload (test_mcarray.cpp:937): half the
+ * host<->device bytes of the f32 call; samples are widened on the device, outputs rounded and saturated to int16. */
+int mcag_process_packed_s16(mcag_proc p, const int16_t *in, long long in_pitch, int nsamples, int16_t *out, long long out_pitch, int *nsamples_out);
 /* Device-resident variant: in / out are device pointers on the handle's device; asynchronous on the handle's stream. */
 int mcag_process_device_f32(mcag_proc p, const float *d_in, long long in_pitch, int nsamples, float *d_out, long long out_pitch, int *nsamples_out);
 

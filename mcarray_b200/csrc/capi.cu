@@ -851,6 +851,20 @@ __global__ void convert_rows_kernel(const Tin *__restrict__ in, long long in_pit
   if (i < n && r < rows) out[(long long)r * out_pitch + i] = (float)in[(long long)r * in_pitch + i];
 }
 
+// synthesised audio float -> the caller's sample type on the device: double widened, int16 rounded to nearest even and saturated
+// (the reference's int16 process() overload narrows the same way through DSPONE)
+template <class Tout> __device__ __forceinline__ Tout narrow_sample(float v);
+template <> __device__ __forceinline__ double narrow_sample<double>(float v) { return (double)v; }
+template <> __device__ __forceinline__ int16_t narrow_sample<int16_t>(float v) {
+  v = rintf(v);
+  return (int16_t)(v > 32767.f ? 32767.f : (v < -32768.f ? -32768.f : v));
+}
+template <class Tout>
+__global__ void convert_out_kernel(const float *__restrict__ in, Tout *__restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = narrow_sample<Tout>(in[i]);
+}
+
 constexpr int kMaxChunks = 8;
 
 // Host-buffer process call.  The streams of the handle are cut into up to kMaxChunks groups; group c+1 is copied host->device
@@ -878,7 +892,7 @@ static int process_host(mcag_proc p, const Tio *const *in, const Tio *in_packed,
 
   float *cur = p->fifo[p->fifo_cur].as<float>();
   if (!is_f32 && nsamples > 0 && p->stage_in.bytes < in_bytes) OK(p->stage_in.alloc(in_bytes));
-  if (want_audio && !is_f32 && nout > 0) OK(ensure_pinned(&p->pin_out, &p->pin_out_bytes, (size_t)B * Cs * nout * 4));
+  if (want_audio && !is_f32 && nout > 0 && p->stage_out.bytes < (size_t)B * Cs * nout * sizeof(Tio)) OK(p->stage_out.alloc((size_t)B * Cs * nout * sizeof(Tio)));
 
   // The FIFO may still be read or carried by work a previous mcag_process_device_f32 call left in flight on the compute stream:
   // the copy-in stream starts behind it.
@@ -914,18 +928,30 @@ static int process_host(mcag_proc p, const Tio *const *in, const Tio *in_packed,
     }
     if (T > 0) OK(run_frames(p, cur, p->fifo_cap, T, b0, b1 - b0));
     if (want_audio && nout > 0) {
+      const float *src = p->out_dev.as<float>() + (long long)b0 * Cs * nout;
+      if constexpr (!is_f32) {
+        // narrow on the device, then copy the caller's sample type straight into the caller's rows
+        const long long cnt = (long long)(b1 - b0) * Cs * nout;
+        Tio *dsto = p->stage_out.as<Tio>() + (long long)b0 * Cs * nout;
+        convert_out_kernel<Tio><<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(src, dsto, cnt);
+        MCAG_CHECK_LAUNCH();
+        p->launches++;
+      }
       CU(cudaEventRecord(p->ev_done[c], st));
       CU(cudaStreamWaitEvent(sout, p->ev_done[c], 0));
-      const float *src = p->out_dev.as<float>() + (long long)b0 * Cs * nout;
-      if (!is_f32) {
-        CU(cudaMemcpyAsync((float *)p->pin_out + (long long)b0 * Cs * nout, src, (size_t)(b1 - b0) * Cs * nout * 4, cudaMemcpyDeviceToHost, sout));
-      } else if (out_packed && Cs == Cout) {
-        CU(cudaMemcpy2DAsync(out_packed + (long long)b0 * Cout * out_pitch, out_pitch * 4, src, (size_t)nout * 4, (size_t)nout * 4, (size_t)(b1 - b0) * Cs, cudaMemcpyDeviceToHost, sout));
+      const Tio *srco = is_f32 ? reinterpret_cast<const Tio *>(src) : p->stage_out.as<Tio>() + (long long)b0 * Cs * nout;
+      if (out_packed && Cs == Cout) {
+        CU(cudaMemcpy2DAsync(out_packed + (long long)b0 * Cout * out_pitch, out_pitch * sizeof(Tio), srco, (size_t)nout * sizeof(Tio), (size_t)nout * sizeof(Tio),
+                             (size_t)(b1 - b0) * Cs, cudaMemcpyDeviceToHost, sout));
+      } else if (out_packed) {   // Cs < Cout: the first Cs rows of every stream, one strided copy per channel
+        for (int ch = 0; ch < Cs; ++ch)
+          CU(cudaMemcpy2DAsync(out_packed + ((long long)b0 * Cout + ch) * out_pitch, (size_t)Cout * out_pitch * sizeof(Tio), srco + (long long)ch * nout,
+                               (size_t)Cs * nout * sizeof(Tio), (size_t)nout * sizeof(Tio), (size_t)(b1 - b0), cudaMemcpyDeviceToHost, sout));
       } else {
         for (int b = b0; b < b1; ++b)
           for (int ch = 0; ch < Cs; ++ch) {
-            Tio *dst = out_packed ? out_packed + ((long long)b * Cout + ch) * out_pitch : out[(long long)b * Cout + ch];
-            if (dst) CU(cudaMemcpyAsync(dst, p->out_dev.as<float>() + ((long long)b * Cs + ch) * nout, (size_t)nout * 4, cudaMemcpyDeviceToHost, sout));
+            Tio *dst = out[(long long)b * Cout + ch];
+            if (dst) CU(cudaMemcpyAsync(dst, srco + ((long long)(b - b0) * Cs + ch) * nout, (size_t)nout * sizeof(Tio), cudaMemcpyDeviceToHost, sout));
           }
       }
     }
@@ -962,18 +988,6 @@ static int process_host(mcag_proc p, const Tio *const *in, const Tio *in_packed,
   CU(cudaStreamSynchronize(st));
   if (want_audio && nout > 0) {
     CU(cudaStreamSynchronize(sout));
-    // f64 / s16 outputs are converted on the host
-    const float *src = (const float *)p->pin_out;
-    for (int b = 0; b < B; ++b)
-      for (int ch = 0; ch < Cs && !is_f32; ++ch) {
-        Tio *dst = out_packed ? out_packed + ((long long)b * Cout + ch) * out_pitch : out[(long long)b * Cout + ch];
-        if (!dst) continue;
-        {
-          const float *s_ = src + ((long long)b * Cs + ch) * nout;
-          if (Conv<Tio>::id == 2) for (int i = 0; i < nout; ++i) { float v = nearbyintf(s_[i]); dst[i] = (Tio)(v > 32767.f ? 32767.f : (v < -32768.f ? -32768.f : v)); }
-          else for (int i = 0; i < nout; ++i) dst[i] = (Tio)s_[i];
-        }
-      }
   }
   if (nsamples_out) *nsamples_out = Cs > 0 ? nout : 0;
   return MCAG_OK;
@@ -992,6 +1006,10 @@ int mcag_process_s16(mcag_proc p, const int16_t *const *in, int nsamples, int16_
 }
 int mcag_process_packed_f32(mcag_proc p, const float *in, long long in_pitch, int nsamples, float *out, long long out_pitch, int *nsamples_out) {
   return process_host<float>(p, nullptr, in, in_pitch, nsamples, nullptr, out, out_pitch, (int)(out_pitch > 0x7fffffff ? 0x7fffffff : out_pitch), nsamples_out);
+}
+
+int mcag_process_packed_s16(mcag_proc p, const int16_t *in, long long in_pitch, int nsamples, int16_t *out, long long out_pitch, int *nsamples_out) {
+  return process_host<int16_t>(p, nullptr, in, in_pitch, nsamples, nullptr, out, out_pitch, (int)(out_pitch > 0x7fffffff ? 0x7fffffff : out_pitch), nsamples_out);
 }
 
 int mcag_process_device_f32(mcag_proc p, const float *d_in, long long in_pitch, int nsamples, float *d_out, long long out_pitch, int *nsamples_out) {

@@ -7,8 +7,12 @@
 //                 of PHAT cross-spectra against steering phasors generated on the fly from fixed-point phase ramps.
 #include "fft.cuh"
 #include "kernels.h"
+#include "tdoa_warp.cuh"
 
+#include <cmath>
+#include <cstdlib>
 #include <type_traits>
+#include <vector>
 
 namespace mcag {
 
@@ -201,6 +205,76 @@ __global__ void __launch_bounds__(G *(N / 16)) tdoa_kernel(const float2 *__restr
                    curves ? curves + ft * P * L : nullptr, lags + ft * P, peaks ? peaks + ft * P : nullptr);
 }
 
+// Analysis phase of the fused kernels: the M windows of frame (b, t) are read straight from the sample rows (coalesced 8-byte loads, the
+// overlapping half is an L2 hit of the neighbouring frame), windowed while packing into the N/2-point complex FFT, post-processed to the
+// one-sided spectrum (optionally written, always its Parseval power) and whitened into s_U.  Channels m = g, g + G, ...; every thread
+// of the CTA calls it, the caller synchronises the CTA afterwards.
+template <int N, int G>
+__device__ __forceinline__ void analysis_phase(const float *__restrict__ x, long long row_pitch, int M, int hop, bool vec_ok, long long ft, int b, int t,
+                                               const float2 *s_w, const float2 *s_tw, const float2 *s_twp, fft_buf_t buf, float2 *s_U, float *s_bv,
+                                               float2 *__restrict__ spec, float *__restrict__ chan_pow, int g, int j, float2 *s_Uf = nullptr) {
+  constexpr int NC = N / 2, TPF = NC / 8, KP = spec_pitch(N), WPF = (TPF + 31) / 32;
+  const int tid = threadIdx.x;
+  for (int m = g; m < M; m += G) {
+    const float *src = x + ((long long)b * M + m) * row_pitch + (long long)t * hop;
+    float2 v[8];
+    if (vec_ok) {
+      const float2 *s2 = reinterpret_cast<const float2 *>(src);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v[r] = __ldg(s2 + j + r * TPF);
+    } else {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) { const int n = j + r * TPF; v[r] = make_float2(src[2 * n], src[2 * n + 1]); }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { const float2 w = s_w[j + r * TPF]; v[r].x *= w.x; v[r].y *= w.y; }
+    fft_run<NC, false>(v, buf, s_twp, j, g);
+    // real post-processing: X[k] = E + W^k O, X[NC-k] = conj(E - W^k O)
+    float2 *U = s_U + (size_t)m * KP;
+    float2 *out = spec ? spec + ((ft * M + m) * KP) : nullptr;
+    float pw = 0.f;
+    for (int k = j; k <= NC / 2; k += TPF) {
+      float2 zk = fft_buf_get(buf, k), zn = fft_buf_get(buf, (NC - k) & (NC - 1));
+      float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+      float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));   // -i/2 (zk - conj zn)
+      float2 w = s_tw[k];   // k <= NC/2: first half of the table, W_N^k itself
+      float2 wo = cmul(w, o);
+      float2 xk = cadd(e, wo), xn = cconj(csub(e, wo));
+      if (k == 0) { xk.y = 0.f; xn.y = 0.f; }
+      if (out) { out[k] = xk; out[NC - k] = xn; }
+      const float wk = (k == 0) ? 1.f : 2.f;
+      pw += wk * (xk.x * xk.x + xk.y * xk.y);
+      if (k != NC - k) pw += wk * (xn.x * xn.x + xn.y * xn.y);
+      const float2 uk = whiten(xk), un = whiten(xn);
+      U[k] = uk;
+      U[NC - k] = un;
+      if (s_Uf) {   // N = 1024 warp lag phase: compact copy of the bins 32 q + 16 (k and NC - k fall into this class together)
+        if ((k & 31) == 16) { s_Uf[m * 16 + (k >> 5)] = uk; s_Uf[m * 16 + ((NC - k) >> 5)] = un; }
+      }
+    }
+    if (j == 0 && out) out[NC + 1] = make_float2(0.f, 0.f);   // pad bin
+    if (chan_pow) {   // Parseval power of the windowed frame, fixed reduction order
+      if constexpr (TPF >= 32) {
+        pw = warp_sum(pw);
+        if ((tid & 31) == 0) s_bv[g * WPF + (j >> 5)] = pw;
+        group_sync<TPF>(g);
+        if (j == 0) {
+          float sacc = 0.f;
+          for (int i = 0; i < WPF; ++i) sacc += s_bv[g * WPF + i];
+          chan_pow[ft * M + m] = sacc / ((float)N * (float)N);
+        }
+      } else {
+        // several transforms share a warp and a neighbour group may be idle this round: shuffle only among this group's lanes
+        const unsigned gmask = (TPF >= 32) ? 0xffffffffu : (((1u << (TPF & 31)) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(TPF - 1)));
+#pragma unroll
+        for (int o2 = TPF / 2; o2 > 0; o2 >>= 1) pw += __shfl_xor_sync(gmask, pw, o2);
+        if (j == 0) chan_pow[ft * M + m] = pw / ((float)N * (float)N);
+      }
+    }
+    group_sync<TPF>(g);
+  }
+}
+
 // Fused STFT -> GCC-PHAT -> lag argmax.  Persistent CTAs walk the (stream, frame) list; per frame a CTA
 //   1. reads the M windows of N samples straight from the sample rows (coalesced 8-byte loads, the overlapping half is an
 //      L2 hit of the neighbouring frame), applies the analysis window while packing into the N/2-point complex FFT,
@@ -239,66 +313,112 @@ __global__ void __launch_bounds__(G *(N / 16), 768 / (G * (N / 16))) stft_tdoa_k
 
   for (long long ft = blockIdx.x; ft < nframes; ft += gridDim.x) {
     const int b = (int)(ft / T), t = (int)(ft - (long long)b * T);
-    // ---- analysis: channels m = g, g + G, ...
-    for (int m = g; m < M; m += G) {
-      const float *src = x + ((long long)b * M + m) * row_pitch + (long long)t * hop;
-      float2 v[8];
-      if (vec_ok) {
-        const float2 *s2 = reinterpret_cast<const float2 *>(src);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) v[r] = __ldg(s2 + j + r * TPF);
-      } else {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) { const int n = j + r * TPF; v[r] = make_float2(src[2 * n], src[2 * n + 1]); }
-      }
-#pragma unroll
-      for (int r = 0; r < 8; ++r) { const float2 w = s_w[j + r * TPF]; v[r].x *= w.x; v[r].y *= w.y; }
-      fft_run<NC, false>(v, buf, s_twp, j, g);
-      // real post-processing: X[k] = E + W^k O, X[NC-k] = conj(E - W^k O)
-      float2 *U = s_U + (size_t)m * KP;
-      float2 *out = spec ? spec + ((ft * M + m) * KP) : nullptr;
-      float pw = 0.f;
-      for (int k = j; k <= NC / 2; k += TPF) {
-        float2 zk = fft_buf_get(buf, k), zn = fft_buf_get(buf, (NC - k) & (NC - 1));
-        float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-        float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));   // -i/2 (zk - conj zn)
-        float2 w = s_tw[k];   // k <= NC/2: first half of the table, W_N^k itself
-        float2 wo = cmul(w, o);
-        float2 xk = cadd(e, wo), xn = cconj(csub(e, wo));
-        if (k == 0) { xk.y = 0.f; xn.y = 0.f; }
-        if (out) { out[k] = xk; out[NC - k] = xn; }
-        const float wk = (k == 0) ? 1.f : 2.f;
-        pw += wk * (xk.x * xk.x + xk.y * xk.y);
-        if (k != NC - k) pw += wk * (xn.x * xn.x + xn.y * xn.y);
-        U[k] = whiten(xk);
-        U[NC - k] = whiten(xn);
-      }
-      if (j == 0 && out) out[NC + 1] = make_float2(0.f, 0.f);   // pad bin
-      if (chan_pow) {   // Parseval power of the windowed frame, fixed reduction order
-        if constexpr (TPF >= 32) {
-          pw = warp_sum(pw);
-          if ((tid & 31) == 0) s_bv[g * WPF + (j >> 5)] = pw;
-          group_sync<TPF>(g);
-          if (j == 0) {
-            float sacc = 0.f;
-            for (int i = 0; i < WPF; ++i) sacc += s_bv[g * WPF + i];
-            chan_pow[ft * M + m] = sacc / ((float)N * (float)N);
-          }
-        } else {
-          // several transforms share a warp and a neighbour group may be idle this round: shuffle only among this group's lanes
-          const unsigned gmask = (TPF >= 32) ? 0xffffffffu : (((1u << (TPF & 31)) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(TPF - 1)));
-#pragma unroll
-          for (int o2 = TPF / 2; o2 > 0; o2 >>= 1) pw += __shfl_xor_sync(gmask, pw, o2);
-          if (j == 0) chan_pow[ft * M + m] = pw / ((float)N * (float)N);
-        }
-      }
-      group_sync<TPF>(g);
-    }
+    analysis_phase<N, G>(x, row_pitch, M, hop, vec_ok, ft, b, t, s_w, s_tw, s_twp, buf, s_U, s_bv, spec, chan_pow, g, j);
     __syncthreads();
     tdoa_pairs<N, G>(s_U, wk, s_twp, buf, s_pair, s_bv, s_bi, P, max_lag, g, j,
                      curves ? curves + ft * P * L : nullptr, lags + ft * P, nullptr);
     __syncthreads();
   }
+}
+
+// The same fused pipeline for N = 1024 with the warp-synchronous lag phase of tdoa_warp.cuh: after the analysis phase every warp takes
+// two pairs at a time (one per half-warp) and runs their decimated inverse transforms in registers.  256 threads: 4 groups of 64 for
+// the forward transforms, 8 warps for the pairs; 2 CTAs per SM (the 32-point register transform needs ~120 registers).
+template <int LCAP>
+__global__ void __launch_bounds__(256, 2) stft_tdoa_warp_kernel(const float *__restrict__ x, long long row_pitch, int B, int T, int M, int hop, int max_lag,
+                                                                const float *__restrict__ win, const float2 *__restrict__ tw_g,
+                                                                const float2 *__restrict__ lag_tab, float2 *__restrict__ spec,
+                                                                float *__restrict__ chan_pow, float *__restrict__ curves, int32_t *__restrict__ lags) {
+  constexpr int N = 1024, G = 4, NC = N / 2, TPF = NC / 8, KP = spec_pitch(N), NT = G * TPF, WPF = TPF / 32, NW = NT / 32;
+  const int P = M * (M - 1) / 2, L = 2 * max_lag + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char *smem = fft_align_smem(smem_raw, 8 * NC);
+  float2 *s_buf = reinterpret_cast<float2 *>(smem);                   // G * NC, each buffer aligned to its size
+  float *s_scr = reinterpret_cast<float *>(s_buf + G * fft_buf_len(NC));   // NW warps x 2 pairs x 16 rows x 32 floats (transpose scratch)
+  float2 *s_U = reinterpret_cast<float2 *>(s_scr + NW * 1024);        // M * KP
+  float2 *s_tw = s_U + (size_t)M * KP;                                // fft_table_len(N)
+  float2 *s_twp = s_tw + NC;
+  float2 *s_w = s_tw + fft_table_len(N);                              // NC (window, pairs of samples)
+  float2 *s_lag = s_w + NC;                                           // kLagTabLen
+  float2 *s_Uf = s_lag + kLagTabLen;                                  // M * 16: bins 32 q + 16 of every channel
+  float *s_bv = reinterpret_cast<float *>(s_Uf + (size_t)M * 16);     // G * WPF
+  unsigned char *s_pair = reinterpret_cast<unsigned char *>(s_bv + G * WPF);   // 2 * P
+
+  const int tid = threadIdx.x;
+  fft_load_tables<N>(s_tw, tw_g, tid, NT);
+  for (int i = tid; i < NC; i += NT) s_w[i] = make_float2(win[2 * i], win[2 * i + 1]);
+  for (int i = tid; i < kLagTabLen; i += NT) s_lag[i] = lag_tab[i];
+  pair_table<N, G>(s_pair, M, P, tid, NT);
+  __syncthreads();
+  const int g = tid / TPF, j = tid % TPF, warp = tid >> 5, half = (tid >> 4) & 1;
+  const fft_buf_t buf = smem_u32(s_buf + g * fft_buf_len(NC));
+  float *scratch = s_scr + warp * 1024 + half * 512;
+  const bool vec_ok = ((row_pitch & 1) == 0) && ((hop & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
+  const long long nframes = (long long)B * T;
+  const int tasks = (P + 1) / 2;
+
+  for (long long ft = blockIdx.x; ft < nframes; ft += gridDim.x) {
+    const int b = (int)(ft / T), t = (int)(ft - (long long)b * T);
+    analysis_phase<N, G>(x, row_pitch, M, hop, vec_ok, ft, b, t, s_w, s_tw, s_twp, buf, s_U, s_bv, spec, chan_pow, g, j, s_Uf);
+    __syncthreads();
+    for (int task = warp; task < tasks; task += NW) {
+      const int p = 2 * task + half;
+      const bool live = p < P;
+      const int pc = live ? p : P - 1;
+      tdoa_pair_halfwarp<LCAP>(s_U, s_Uf, s_lag, scratch, s_pair[2 * pc], s_pair[2 * pc + 1], live, pc, max_lag,
+                               curves ? curves + ft * P * L : nullptr, lags + ft * P, nullptr);
+    }
+    __syncthreads();
+  }
+}
+
+// lag-phase table of tdoa_warp.cuh, one copy per device (double precision on the host)
+static const float2 *lag_table_device() {
+  static float2 *tabs[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!tabs[dev]) {
+    std::vector<float2> h(kLagTabLen);
+    for (int i = 0; i < 32; ++i)
+      for (int s = 0; s < 16; ++s) {
+        // weight 1/2 on sub-sequence 0 (it is its own Hermitian partner); row 1 is read as the per-lag ROTATION of the recurrence: no weight
+        const double a1 = 2.0 * M_PI * (double)(s * i) / 1024.0, w = (s == 0 && i != 1) ? 0.5 : 1.0;
+        const double a2 = 2.0 * M_PI * (double)((32 * s + 16) * i) / 1024.0;
+        h[i * 16 + s] = make_float2((float)(w * std::cos(a1)), (float)(w * std::sin(a1)));
+        h[512 + i * 16 + s] = make_float2((float)std::cos(a2), (float)std::sin(a2));
+      }
+    float2 *d = nullptr;
+    if (cudaMalloc(&d, sizeof(float2) * kLagTabLen) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, h.data(), sizeof(float2) * kLagTabLen, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+    tabs[dev] = d;
+  }
+  return tabs[dev];
+}
+
+template <int LCAP>
+static int launch_stft_tdoa_warp(const float *x, long long row_pitch, int B, int T, int M, int hop, int max_lag, const float *win, const float2 *tw,
+                                 float2 *spec, float *chan_pow, float *curves, int32_t *lags, cudaStream_t st) {
+  constexpr int N = 1024, NC = 512, G = 4, NW = 8;
+  const int P = M * (M - 1) / 2;
+  const float2 *lag_tab = lag_table_device();
+  if (!lag_tab) return mcag_set_error(2, "tdoa: could not create the lag table");
+  size_t smem = sizeof(float2) * ((size_t)M * spec_pitch(N) + fft_table_len(N) + (size_t)G * fft_buf_len(NC) + NC + kLagTabLen + (size_t)M * 16) + 4 * NW * 1024 +
+                4 * G * 2 + 2 * P + 16 + 8 * NC /* buffer alignment slack */;
+  if (smem > 110 * 1024) return -1;   // more microphones than two CTAs per SM can stage: the caller falls back to the general kernel
+  auto kern = stft_tdoa_warp_kernel<LCAP>;
+  static int sm_count = 0, dev_cached = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != dev_cached) { cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); dev_cached = dev; }
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
+  if (per_sm < 1) per_sm = 1;
+  const long long nframes = (long long)B * T;
+  const long long grid = nframes < (long long)sm_count * per_sm ? nframes : (long long)sm_count * per_sm;
+  kern<<<(unsigned)grid, 256, smem, st>>>(x, row_pitch, B, T, M, hop, max_lag, win, tw, lag_tab, spec, chan_pow, curves, lags);
+  MCAG_CHECK_LAUNCH();
+  return 0;
 }
 
 template <int N> static int launch_tdoa(const float2 *spec, int B, int T, int M, int max_lag, const float2 *tw, float *curves, int32_t *lags,
@@ -360,6 +480,11 @@ int k_stft_tdoa(const float *x, long long row_pitch, int B, int T, int M, int N,
   if (M < 2 || M > 255) return mcag_set_error(1, "tdoa: need 2..255 channels");
   if (max_lag < 0 || max_lag > N / 2 - 1) return mcag_set_error(1, "tdoa: max_lag out of range");
   if (hop <= 0 || hop > N) return mcag_set_error(1, "tdoa: bad hop");
+  if (N == 1024 && max_lag <= 31 && !getenv("MCAG_TDOA_GENERAL")) {   // warp-synchronous decimated lag phase (tdoa_warp.cuh)
+    const int rc = max_lag <= 28 ? launch_stft_tdoa_warp<28>(x, row_pitch, B, T, M, hop, max_lag, win, tw, spec, chan_pow, curves, lags, st)
+                                 : launch_stft_tdoa_warp<31>(x, row_pitch, B, T, M, hop, max_lag, win, tw, spec, chan_pow, curves, lags, st);
+    if (rc >= 0) return rc;
+  }
   switch (N) {
     case 256: return launch_stft_tdoa<256>(x, row_pitch, B, T, M, hop, max_lag, win, tw, spec, chan_pow, curves, lags, st);
     case 512: return launch_stft_tdoa<512>(x, row_pitch, B, T, M, hop, max_lag, win, tw, spec, chan_pow, curves, lags, st);

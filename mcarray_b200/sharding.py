@@ -75,6 +75,7 @@ class ShardedSrpPhat:
         # torch view of the handle's own CUDA stream: the pack kernel, the all-reduce and the unpack are stream-ordered behind the
         # SRP kernels, so a step needs no host synchronisation
         self.stream = torch.cuda.ExternalStream(capi.lib().mcag_stream(self.local.handle), device=dev)
+        self.time_allreduce, self._ar_events = False, []     # bench.py: CUDA events around the collective on the handle's stream
 
     def _reduce(self):
         from . import capi
@@ -86,9 +87,21 @@ class ShardedSrpPhat:
             if rows:
                 capi.check(lib.mcag_k_argmax_pack(C.c_void_p(lib.mcag_device_ptr(p.handle, capi.OUT_ENERGY)), C.c_longlong(rows), p.info.n_dirs, self.d0,
                                                   capi.vp(packed), C.c_void_p(lib.mcag_stream(p.handle))))
+                if self.time_allreduce:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(self.stream)
                 allreduce_argmax(packed, self.group)
+                if self.time_allreduce:
+                    e1.record(self.stream)
+                    self._ar_events.append((e0, e1))
             val, idx = unpack_max(packed)
         return val.view(p.info.n_streams, p.frames_done), idx.view(p.info.n_streams, p.frames_done)   # explicit shape: a call may complete 0 frames
+
+    def allreduce_ms(self):
+        """mean device time of the all-reduce since the last call (needs time_allreduce); synchronises the stream"""
+        self.stream.synchronize()
+        ev, self._ar_events = self._ar_events, []
+        return float(np.mean([a.elapsed_time(b) for a, b in ev])) if ev else None
 
     def process(self, x):
         """x [B*M][n] host array (identical on every rank) -> (peak energy [B][T], global direction cell [B][T]) on every rank."""

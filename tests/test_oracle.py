@@ -175,7 +175,7 @@ def test_bench_reference_arm_prints_the_contract_line():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--cpu-frames", "8", "--cpu-streams-per-core", "1"], capture_output=True, text=True, timeout=600)
+                          "--frames", "8", "--streams", "8"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     for key in ("metric", "value", "unit", "impl", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data",
@@ -184,3 +184,9 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["metric"] == "channel_samples_per_sec" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    # the config object is the GPU arm's: same keys, same batch (the driver compares the two arms' configs)
+    sys.path.insert(0, root)
+    import bench
+    wl = bench.WORKLOADS["cfg2"]()
+    assert line["config"] == bench.config_of(wl, 8, 8, 1)
+    assert bench.config_of(wl, wl.B_default, wl.T_default, 1)["frames_per_stream_per_step"] == 750

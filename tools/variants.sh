@@ -18,7 +18,7 @@ else
   w=$1; shift
   cd ../..
   for tag in "$@"; do
-    MCAG_LIB_PATH=$PWD/mcarray_b200/variants/lib_$tag.so python bench.py --workload $w --no-cpu-baseline --no-e2e --steps 30 2>&1 | tail -1 | python -c "
+    MCAG_LIB_PATH=$PWD/mcarray_b200/variants/lib_$tag.so python bench.py --workload $w --no-cpu-baseline --no-e2e --also none --sustain 0 --steps 30 2>&1 | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); r=d['roofline']
 print('$tag $w', 'ms/step %.4f' % d['ms_per_step'], {k: round(v,4) for k,v in r['kernels_ms_per_step'].items()})"
