@@ -271,7 +271,7 @@ class Cfg1Mask(Workload):
     def kernel_bytes_per_frame(self):
         K, hop, nb = self.N // 2 + 1, self.hop, 45
         return {"stft": 4 * 2 * hop + 8 * 2 * K, "mask_stats": 8 * 2 * K + 4 * 6 * nb, "mask_scan": 4 * 6 * nb + 4 * 2 * nb, "mask_apply": 2 * 8 * 2 * K + 4 * 2 * nb,
-                "istft": 8 * 2 * K + 4 * 2 * hop}
+                "istft": 8 * 2 * K + 4 * 2 * hop, "mask_fused": 4 * 2 * hop + 4 * 2 * hop + 8}   # fused: samples in, samples out, frame powers
 
     def pipeline_bytes_per_frame(self):
         return 4 * 2 * self.hop + 4 * 2 * self.hop                    # samples in, samples out
@@ -435,7 +435,7 @@ class ClockSampler:
 
 def profile_read(p, reset=True):
     from mcarray_b200 import capi
-    n = 14
+    n = 32                                                         # >= MCAG_PROF_COUNT; names past the count are empty
     ms = (C.c_double * n)()
     cnt = (C.c_longlong * n)()
     capi.check(capi.lib().mcag_profile_read(p.handle, ms, cnt, C.c_int(int(reset))))

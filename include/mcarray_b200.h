@@ -76,7 +76,9 @@ enum {
 
 enum {                    /* emit flags: keep optional intermediates of the last call fetchable */
   MCAG_EMIT_CORR = 1, MCAG_EMIT_CURVES = 2,
-  MCAG_EMIT_SPECTRA = 4   /* TDOA only: its fused STFT->GCC kernel keeps the spectra on chip unless this is set (every other kind always has them) */
+  MCAG_EMIT_SPECTRA = 4,  /* TDOA, MASK: their fused kernels keep the spectra on chip unless this is set (every other kind always has them); MASK
+                             then runs the staged stft / stats / scan / apply / istft kernels and MCAG_OUT_SPECTRA / _BEAMS become fetchable */
+  MCAG_EMIT_MASK_TRACE = 8 /* MASK: keep MCAG_OUT_MASK_Q / MCAG_OUT_MASK_DEC of the last call (always kept by the staged path) */
 };
 
 typedef struct {
@@ -173,6 +175,7 @@ long long mcag_kernel_launches(mcag_proc p);              /* kernels launched by
 enum {
   MCAG_PROF_STFT = 0, MCAG_PROF_GATE, MCAG_PROF_GCC_TAU, MCAG_PROF_ENERGY, MCAG_PROF_SELECT_DOA, MCAG_PROF_DS_SELECT, MCAG_PROF_ISTFT,
   MCAG_PROF_CURVE_SCAN, MCAG_PROF_TDOA, MCAG_PROF_DS_FAN, MCAG_PROF_SRP, MCAG_PROF_MASK_STATS, MCAG_PROF_MASK_SCAN, MCAG_PROF_MASK_APPLY,
+  MCAG_PROF_MASK_FUSED,
   MCAG_PROF_COUNT
 };
 int mcag_profile_enable(mcag_proc p, int on);
@@ -212,8 +215,9 @@ int mcag_k_select_doa(const float *d_energy, long long BT, int D, int n_pairs, i
  * ordered(E) << 31 | (0x7FFFFFFF - d): an int64 MAX all-reduce over the slices of a sharded grid gives the global arg-max cell */
 int mcag_k_argmax_pack(const float *d_map, long long rows, int D, int d_offset, long long *d_packed, void *stream);
 int mcag_k_ds_fan(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_steer_fx, int D, void *d_out, void *stream);
-/* the fan on the tensor cores (tcgen05, 3xTF32; M in {16, 32, 48, 64}, other counts run mcag_k_ds_fan).  Same results; measured 4x
- * slower than mcag_k_ds_fan on B200 for the [B][T][D][K] beam layout (scattered 8-byte stores), so the processors do not use it. */
+/* the fan on the tensor cores (tcgen05, 3xTF32; M in {16, 32, 48, 64}, other counts run mcag_k_ds_fan): four consecutive bins of a
+ * (128-frame, 64-direction) tile stay resident in TMEM, so every (frame, direction) leaves as 32 contiguous bytes of its [B][T][D][K] row.
+ * What MCAG_KIND_DSFAN runs for those microphone counts.  The pad bin of d_spec rows must be zero (it is, for spectra of this library). */
 int mcag_k_ds_fan_tensor(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_steer_fx, int D, void *d_out, void *stream);
 int mcag_k_srp_channel(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_mic_fx, int D, float *d_srp, void *stream);
 int mcag_k_srp_tensor(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_mic_fx, int D, float *d_srp, void *stream);

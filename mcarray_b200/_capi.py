@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("MCAG_LIB_PATH") or os.path.join(_HERE, "libmcarray_b2
 KIND_SSL, KIND_SL, KIND_FREQGCC, KIND_MASK, KIND_TDOA, KIND_DSFAN, KIND_SRP, KIND_MULTIBAND = range(8)
 (OUT_SPECTRA, OUT_POWER_DB, OUT_CORR, OUT_ENERGY, OUT_CELL, OUT_PROB, OUT_LAGS, OUT_CURVES, OUT_ACTIVE, OUT_BEAMS,
  OUT_MASK_Q, OUT_MASK_DEC, OUT_BAND_CELL, OUT_TRACK_DOA) = range(14)
-EMIT_CORR, EMIT_CURVES, EMIT_SPECTRA = 1, 2, 4
+EMIT_CORR, EMIT_CURVES, EMIT_SPECTRA, EMIT_MASK_TRACE = 1, 2, 4, 8
 
 c_dp = C.POINTER(C.c_double)
 

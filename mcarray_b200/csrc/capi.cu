@@ -192,7 +192,8 @@ struct mcag_proc_s {
   DevBuf steer_fx, steer_tab, beams, tail[2], out_dev; int tail_cur = 0;
   DevBuf lags, curves, curve_state, fg, est, track_doa, track_prob;
   DevBuf mic_fx, srp_ws;
-  DevBuf H, H2, thr, stats, gains, Q, noise, dec, qtrace;
+  DevBuf H, H2, thr, stats, gains, Q, noise, dec, qtrace, band_lohi, bin_lohi;
+  bool mask_fused = false;   // MASK: analysis + mask + synthesis in one kernel (mask_fused.cu)
   DevBuf band_raw, band_energy, floor_pow, band_cells, mb_raw_cell, mb_raw_prob, mb_lohi;
   int mb_bw = 0, mb_kmin = 0, mb_kmax = 0; bool mb_fused = false;   // band supports (host copy of what mb_band_kernel derives from H)
   void *pin_in = nullptr, *pin_out = nullptr; size_t pin_in_bytes = 0, pin_out_bytes = 0;
@@ -334,7 +335,11 @@ int mcag_create(const mcag_config *cfg, mcag_proc *out) {
   // FIFO: carried samples (< N) + one call's worth of new samples; a call completing Tmax frames consumes Tmax*hop
   p->fifo_cap = ((long long)N + (long long)(T + 1) * p->hop + 3) & ~3LL;
   for (int i = 0; i < 2; ++i) if ((rc = p->fifo[i].alloc(sizeof(float) * p->rows * p->fifo_cap))) return fail(rc);
-  if (kind != MCAG_KIND_TDOA || (cfg->emit & MCAG_EMIT_SPECTRA))
+  // MASK: one fused kernel (spectra stay on chip) unless the caller wants the spectra, the method is NOTHING (a plain analysis /
+  // synthesis pass) or the shape is outside the fused kernel; MCAG_MASK_STAGED=1 forces the staged kernels (tests compare the two)
+  p->mask_fused = kind == MCAG_KIND_MASK && !(cfg->emit & MCAG_EMIT_SPECTRA) && cfg->mask_method != 5 && k_mask_fused_supported(N, cfg->hop, cfg->n_bands) &&
+                  !getenv("MCAG_MASK_STAGED");
+  if ((kind != MCAG_KIND_TDOA && !p->mask_fused) || (cfg->emit & MCAG_EMIT_SPECTRA))
     if ((rc = p->spec.alloc(sizeof(float2) * B * T * M * KP))) return fail(rc);
   if ((rc = p->chan_pow.alloc(sizeof(float) * B * T * M))) return fail(rc);
   if ((rc = p->power_db.alloc(sizeof(float) * B * T))) return fail(rc);
@@ -446,7 +451,8 @@ int mcag_create(const mcag_config *cfg, mcag_proc *out) {
       if ((rc = p->srp_ws.alloc(k_srp_tensor_workspace_bytes((long long)B * T, p->M, N, p->D)))) return fail(rc);
   }
   if (p->Cs > 0) {
-    if ((rc = p->beams.alloc(sizeof(float2) * B * T * (kind == MCAG_KIND_MASK ? 2 : p->Cs) * KP))) return fail(rc);
+    if (kind != MCAG_KIND_MASK)   // MASK masks the analysis spectra in place (staged) or never materialises them (fused)
+      if ((rc = p->beams.alloc(sizeof(float2) * B * T * p->Cs * KP))) return fail(rc);
     for (int i = 0; i < 2; ++i) if ((rc = p->tail[i].alloc(sizeof(float) * B * p->Cs * (N - p->hop)))) return fail(rc);
     if ((rc = p->out_dev.alloc(sizeof(float) * B * p->Cs * T * p->hop))) return fail(rc);
   }
@@ -460,10 +466,27 @@ int mcag_create(const mcag_config *cfg, mcag_proc *out) {
     }
     if ((rc = upload(p->H, H.data(), H.size() * 4, st)) || (rc = upload(p->H2, H2.data(), H2.size() * 4, st)) || (rc = upload(p->thr, thr.data(), nb * 4, st)))
       return fail(rc);
+    // band supports [lo, hi) per band and covering bands [lo, hi) per bin, as mask_stats_kernel / mask_apply_kernel derive them
+    std::vector<int> blh(2 * nb);
+    std::vector<unsigned char> klh(2 * (size_t)p->K);
+    for (size_t b = 0; b < nb; ++b) {
+      int lo = p->K, hi = 0;
+      for (int k = 0; k < p->K; ++k) if (H2[b * KP + k] != 0.f) { lo = std::min(lo, k); hi = k + 1; }
+      blh[2 * b] = lo; blh[2 * b + 1] = hi;
+    }
+    for (int k = 0; k < p->K; ++k) {
+      int lo = (int)nb, hi = 0;
+      for (size_t b = 0; b < nb; ++b) if (H[b * KP + k] != 0.f) { lo = std::min(lo, (int)b); hi = (int)b + 1; }
+      klh[2 * k] = (unsigned char)lo; klh[2 * k + 1] = (unsigned char)hi;
+    }
+    if (nb > 255) p->mask_fused = false;
+    if ((rc = upload(p->band_lohi, blh.data(), blh.size() * sizeof(int), st)) || (rc = upload(p->bin_lohi, klh.data(), klh.size(), st))) return fail(rc);
     CUF(cudaStreamSynchronize(st));
-    if ((rc = p->stats.alloc(4 * B * T * nb * 6)) || (rc = p->gains.alloc(4 * B * T * nb * 2)) || (rc = p->Q.alloc(4 * B * nb)) ||
-        (rc = p->noise.alloc(4 * B * nb)) || (rc = p->dec.alloc(B * T * nb)) || (rc = p->qtrace.alloc(4 * B * T * nb)))
-      return fail(rc);
+    if ((rc = p->Q.alloc(4 * B * nb)) || (rc = p->noise.alloc(4 * B * nb))) return fail(rc);
+    if (!p->mask_fused)
+      if ((rc = p->stats.alloc(4 * B * T * nb * 6)) || (rc = p->gains.alloc(4 * B * T * nb * 2))) return fail(rc);
+    if (!p->mask_fused || (cfg->emit & MCAG_EMIT_MASK_TRACE))
+      if ((rc = p->dec.alloc(B * T * nb)) || (rc = p->qtrace.alloc(4 * B * T * nb))) return fail(rc);
   }
   if ((rc = init_state(p))) return fail(rc);
   *out = p;
@@ -481,7 +504,7 @@ void mcag_destroy(mcag_proc p) {
                    &p->active, &p->gate, &p->pair_fx, &p->corr, &p->esum, &p->energy, &p->energy_state, &p->raw_idx, &p->raw_prob, &p->cells,
                    &p->prob, &p->cell_state, &p->prob_state, &p->steer_fx, &p->steer_tab, &p->beams, &p->tail[0], &p->tail[1], &p->out_dev,
                    &p->lags, &p->curves, &p->curve_state, &p->fg, &p->est, &p->track_doa, &p->track_prob, &p->mic_fx, &p->srp_ws, &p->H, &p->H2, &p->thr, &p->stats, &p->gains, &p->Q,
-                   &p->noise, &p->dec, &p->qtrace, &p->band_raw, &p->band_energy, &p->floor_pow, &p->band_cells, &p->mb_raw_cell, &p->mb_raw_prob, &p->mb_lohi};
+                   &p->noise, &p->dec, &p->qtrace, &p->band_lohi, &p->bin_lohi, &p->band_raw, &p->band_energy, &p->floor_pow, &p->band_cells, &p->mb_raw_cell, &p->mb_raw_prob, &p->mb_lohi};
   for (DevBuf *b : all) b->release();
   for (auto &r : p->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (cudaEvent_t e : p->prof_pool) cudaEventDestroy(e);
@@ -525,7 +548,7 @@ void *mcag_stream(mcag_proc p) { return p ? (void *)p->stream : nullptr; }
 long long mcag_kernel_launches(mcag_proc p) { return p ? p->launches : 0; }
 
 static const char *const k_prof_names[MCAG_PROF_COUNT] = {"stft", "gate", "gcc_tau", "energy", "select_doa", "ds_select", "istft", "curve_scan",
-                                                        "stft_gcc", "ds_fan", "srp", "mask_stats", "mask_scan", "mask_apply"};
+                                                        "stft_gcc", "ds_fan", "srp", "mask_stats", "mask_scan", "mask_apply", "mask_fused"};
 const char *mcag_profile_name(int id) { return (id >= 0 && id < MCAG_PROF_COUNT) ? k_prof_names[id] : ""; }
 int mcag_profile_enable(mcag_proc p, int on) {
   if (!p) return mcag_set_error(MCAG_ERR_INVALID, "null handle");
@@ -597,6 +620,28 @@ static int run_frames(mcag_proc p, const float *x_all, long long pitch, int T, i
   unsigned char *active = p->active.as<unsigned char>() + o * T;
   const float *win = p->win.as<float>();
   const float2 *tw = p->tw.as<float2>();
+  if (kind == MCAG_KIND_MASK && p->mask_fused) {
+    // analysis + FastBinauralMasking + synthesis in one kernel: spectra, band statistics and gains never leave the SM
+    {
+      PROF(MCAG_PROF_MASK_FUSED);
+      const int nb_ = p->cfg.n_bands;
+      const long long ov = N - hop;
+      float *outp = ext_out ? ext_out + o * ext_rows * ext_pitch : p->out_dev.as<float>() + o * 2 * T * hop;
+      OK(k_mask_fused(x, pitch, B, T, N, hop, win, tw, p->H.as<float>(), p->H2.as<float>(), p->band_lohi.as<int>(), p->bin_lohi.as<unsigned char>(), nb_,
+                      p->cfg.mask_method, p->cfg.mask_alg, p->thr.as<float>(), p->Q.as<float>() + o * nb_, p->noise.as<float>() + o * nb_,
+                      (int)(p->frames_total > 2 ? 2 : p->frames_total), p->tail[p->tail_cur].as<float>() + o * 2 * ov,
+                      p->tail[p->tail_cur ^ 1].as<float>() + o * 2 * ov, outp, ext_out ? ext_pitch : (long long)T * hop, ext_out ? ext_rows : 2, chan_pow,
+                      p->dec.p ? p->dec.as<unsigned char>() + o * T * nb_ : nullptr, p->qtrace.p ? p->qtrace.as<float>() + o * T * nb_ : nullptr, st));
+      p->launches++;
+    }
+    PROF(MCAG_PROF_GATE);
+    const int needed = (int)(p->cfg.floor_seconds * (float)p->cfg.sample_rate);
+    gate_kernel<<<B, 256, 0, st>>>(chan_pow, chan_raw, B, T, M, N, p->cfg.use_power_floor, p->cfg.floor_ccs_power, p->cfg.noise_margin_db, needed,
+                                   p->gate.as<GateState>() + o, p->power_db.as<float>() + o * T, active, nullptr);
+    MCAG_CHECK_LAUNCH();
+    p->launches++;
+    return MCAG_OK;
+  }
   if (kind == MCAG_KIND_TDOA) {
     // fused STFT -> GCC-PHAT -> lag argmax: the spectra stay in shared memory unless MCAG_EMIT_SPECTRA asks for them
     PROF(MCAG_PROF_TDOA);
@@ -735,9 +780,12 @@ static int run_frames(mcag_proc p, const float *x_all, long long pitch, int T, i
     }
   } else if (kind == MCAG_KIND_DSFAN) {
     PROF(MCAG_PROF_DS_FAN);
-    // CUDA cores on purpose: the tcgen05 variant (mcag_k_ds_fan_tensor) is 4x slower here, because the bin index is the batch index of
-    // the contraction and a tile never holds consecutive bins of one beam (scattered 8-byte stores)
-    OK(k_ds_fan(spec, B, T, M, N, p->steer_fx.as<uint64_t>(), D, p->beams.as<float2>() + o * T * D * KP, st));
+    // 16 / 32 / 48 / 64 microphones: the contraction runs on the tensor cores with four consecutive bins of a tile resident in TMEM
+    // (fan_tc.cu); other counts take the CUDA-core register-tile kernel.  MCAG_FAN_CUDA_CORES=1 forces the latter (tests compare the two).
+    if (k_ds_fan_tensor_supported(M) && !getenv("MCAG_FAN_CUDA_CORES"))
+      OK(k_ds_fan_tensor(spec, B, T, M, N, p->steer_fx.as<uint64_t>(), D, p->beams.as<float2>() + o * T * D * KP, st));
+    else
+      OK(k_ds_fan(spec, B, T, M, N, p->steer_fx.as<uint64_t>(), D, p->beams.as<float2>() + o * T * D * KP, st));
     p->launches++;
   } else if (kind == MCAG_KIND_SRP) {
     {

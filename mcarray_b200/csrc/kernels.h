@@ -46,9 +46,9 @@ size_t k_srp_tensor_workspace_bytes(long long BT, int M, int N, int D);
 int k_srp_tensor_ws(const float2 *spec, int B, int T, int M, int N, const uint64_t *mic_fx, int D, float *srp, void *workspace, size_t ws_bytes,
                     cudaStream_t st);
 int k_srp_tensor(const float2 *spec, int B, int T, int M, int N, const uint64_t *mic_fx, int D, float *srp, cudaStream_t st);
-size_t k_ds_fan_tensor_workspace_bytes(long long BT, int M, int N);
-int k_ds_fan_tensor_ws(const float2 *spec, int B, int T, int M, int N, const uint64_t *steer_fx, int D, float2 *out, void *workspace, size_t ws_bytes,
-                       cudaStream_t st);
+
+// fan_tc.cu (tcgen05): the delay-and-sum fan, four bins of a (frame, direction) tile resident in TMEM
+bool k_ds_fan_tensor_supported(int M);
 int k_ds_fan_tensor(const float2 *spec, int B, int T, int M, int N, const uint64_t *steer_fx, int D, float2 *out, cudaStream_t st);
 
 // mask.cu
@@ -56,6 +56,13 @@ int k_mask_stats(const float2 *spec, long long BT, int N, const float *H2, int n
 int k_mask_scan(const float *stats, int B, int T, int N, int nb, int method, int alg, const float *thresholds, float *Q, float *noise,
                 int first_call, float *gains, unsigned char *decisions, float *q_trace, cudaStream_t st);
 int k_mask_apply(float2 *spec, long long BT, int N, const float *H, int nb, const float *gains, cudaStream_t st);
+
+// mask_fused.cu: analysis + FastBinauralMasking + synthesis in one kernel, spectra never leave the SM (hop = N/2, N >= 512)
+bool k_mask_fused_supported(int N, int hop, int nb);
+int k_mask_fused(const float *x, long long row_pitch, int B, int T, int N, int hop, const float *win, const float2 *tw, const float *H, const float *H2,
+                 const int *band_lohi, const unsigned char *bin_lohi, int nb, int method, int alg, const float *thresholds, float *Q, float *noise,
+                 int first_call, const float *tail_in, float *tail_out, float *out, long long out_pitch, int out_rows, float *chan_pow,
+                 unsigned char *decisions, float *q_trace, cudaStream_t st);
 
 // multiband.cu
 int k_mb_band(const float2 *spec, long long BT, int N, const float *H, int nb, const float2 *W, int D, float *band_raw, float *band_energy,

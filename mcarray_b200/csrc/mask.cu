@@ -5,10 +5,9 @@
 //   apply  : out[k] = X[k] * sum_b gain_b * H_b[k]  (gain only on bins 0..N/2-1, the Nyquist bin is summed unmasked)
 #include "common.cuh"
 #include "kernels.h"
+#include "mask_common.cuh"
 
 namespace mcag {
-
-constexpr int MS_NSTAT = 6;   // pw2, num, eL, eR, pL, pR
 
 // The mel bands are narrow (a triangular filter covers a few per cent of the bins), so every kernel first finds the non-zero bin
 // range of each band (and the band range of each bin) from the coefficient table; the frame loops then touch only those.
@@ -67,51 +66,17 @@ __global__ void mask_scan_kernel(const float *__restrict__ stats, int B, int T, 
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * nb) return;
   const int s = i / nb, b = i - s * nb;
-  const float K = (float)(N / 2 + 1), NH = (float)(N / 2);
-  const float lam = 0.04f, keep = 1.0f - 0.04f, reject = 0.999f, rho = 0.01f;   // FastBinauralMasking.h:114,122,126
   float Q = Qs[i], noise = noise_s[i];
   const float thr = thresholds[b];
   for (int t = 0; t < T; ++t) {
     const long long bt = (long long)s * T + t;
-    const float *st = stats + (bt * nb + b) * MS_NSTAT;
-    const float pw = sqrtf(st[0] / NH);
-    Q = Q * lam + keep * pw;                                        // temportalMasking :489
-    bool temp = pw < reject * Q;                                    // :492
-    bool spat = false;
-    if (alg == 0 || alg == 1) {                                     // BOTH / SPATIAL :159-166
-      const float num = st[1] / K;
-      float ncorr;
-      if (num == 0.f) ncorr = 0.f;
-      else { const float den = sqrtf((st[2] / K) * (st[3] / K)); ncorr = (den == 0.f) ? 1.f : num / den; }
-      spat = ncorr < thr;                                           // :374
-      if (alg == 1) temp = false;
-    }
-    float gl = 1.f, gr = 1.f;                                       // enhanceFrame: _enhanceFactor = 1
-    const int dec = spat ? 2 : (temp ? 1 : 0);
-    if (dec) {
-      switch (method) {
-        case 3: gl = gr = 1.0f / 1000.0f; break;                    // FULL  :214-217
-        case 0: gl = gr = 1.0f / (spat ? 10.0f : 3.0f); break;      // FACTOR :284-287, .h:117-118
-        case 1: {                                                   // RELATIVE :246-282 (uses the updated Q)
-          if (Q < 1e-10f) gl = gr = sqrtf(rho);
-          else { gl = sqrtf((st[2] / K) * rho / Q); gr = sqrtf((st[3] / K) * rho / Q); }
-        } break;
-        case 4: {                                                   // NOISY :220-243
-          if (first_call >= 2) {
-            const float pl = sqrtf(st[4] / NH), pr = sqrtf(st[5] / NH);
-            gl = pl > 0.f ? noise / pl : 1.f;
-            gr = pr > 0.f ? noise / pr : 1.f;
-          }
-        } break;
-        default: break;
-      }
-    }
+    float gl, gr;
+    const int dec = mask_band_step(stats + (bt * nb + b) * MS_NSTAT, N, method, alg, thr, first_call, Q, noise, gl, gr);
     gains[(bt * nb + b) * 2] = gl;
     gains[(bt * nb + b) * 2 + 1] = gr;
     if (decisions) decisions[bt * nb + b] = (unsigned char)dec;
     if (q_trace) q_trace[bt * nb + b] = Q;
     ++first_call;                                                   // :193-197
-    if (first_call < 2) noise = Q;
   }
   Qs[i] = Q; noise_s[i] = noise;   // the frame counter (_firstCall) is common to all streams and lives on the host
 }

@@ -25,8 +25,7 @@
 // A second small kernel adds the partial maps in a fixed order (deterministic) and applies the -nz/2 term.
 #include "common.cuh"
 #include "kernels.h"
-
-#include <cuda.h>
+#include "tc_common.cuh"
 
 #define OK_RC(call)        \
   do {                     \
@@ -47,85 +46,8 @@ constexpr int TC_B_BYTES = 2 * TC_BD * TC_KC * 4;      // 32 KB
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 96 KB
 constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
 
-// ---- PTX wrappers -------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// bounded spin: a pipeline bug traps instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
-  uint32_t done = 0;
-  for (uint32_t spin = 0; !done; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (spin > (1u << 26)) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N = 256, M = 128
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
-
-// hi part of the 3xTF32 split: x rounded to the nearest TF32 (add half a TF32 ulp to the bit pattern, clear the low 13 bits: two
-// ALU operations; cvt.rna.tf32.f32 does the same on the quarter-rate conversion pipe and slowed the producers by 20 %).  With a
-// rounded hi, lo = x - hi is at most half a TF32 ulp and has no preferred sign; with a truncated hi the dropped lo*lo products
-// all carry the sign of the full product and bias |Y|^2 low by ~2^-22 of the sum over bins.
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
-
 // ---- pre-pass: whiten, split, transpose to bin-major --------------------------------------------------------------------
 // spec [BT][M][KP] float2  ->  U_hi / U_lo [K][BTpad][2M] fp32 (rows t >= BT stay zero), nzsum[t] = sum_k #(non-zero channels)
-// WHITEN = false keeps the raw spectra (delay-and-sum fan): same layout, no PHAT, no non-zero count.
-template <bool WHITEN>
 __global__ void __launch_bounds__(256) srp_prepare_kernel(const float2 *__restrict__ spec, long long BT, long long BTpad, int M, int N,
                                                            float *__restrict__ Uhi, float *__restrict__ Ulo, float *__restrict__ nzsum) {
   __shared__ float2 s_t[32][65];   // [bin in chunk][mic], M <= 64
@@ -149,10 +71,8 @@ __global__ void __launch_bounds__(256) srp_prepare_kernel(const float2 *__restri
       float2 u = make_float2(0.f, 0.f);
       if (k < K) {
         u = spec[(t * M + m) * KP + k];
-        if (WHITEN) {
-          u = whiten(u);
-          nz += (u.x != 0.f || u.y != 0.f) ? 1.f : 0.f;
-        }
+        u = whiten(u);
+        nz += (u.x != 0.f || u.y != 0.f) ? 1.f : 0.f;
       }
       s_t[lane][m] = u;
     }
@@ -169,7 +89,6 @@ __global__ void __launch_bounds__(256) srp_prepare_kernel(const float2 *__restri
     }
     __syncthreads();
   }
-  if (!WHITEN) return;
   nz = warp_sum(nz);
   if (lane == 0) s_nz[warp] = nz;
   __syncthreads();
@@ -187,15 +106,10 @@ struct TcParams {
   int n_tt, n_dt, n_ks;  // frame tiles, direction tiles, bin ranges
   int bins_per_range;
   const uint64_t *mic_fx;   // [D][M] 0.64 fixed-point turns per bin
-  float *partial;           // [n_ks][BT][D]                      (SRP: partial energy maps)
-  float2 *beams;            // [BT][D][KP] complex beam spectra   (delay-and-sum fan)
-  int KP;                   // spectrum pitch of `beams`
-  float out_scale;          // 1 / M
+  float *partial;           // [n_ks][BT][D] partial energy maps
 };
 
-// FAN = true is the delay-and-sum fan of Beamformer::processFrame (Beamformer.cpp:51-71) steered to every direction of the tile: the
-// same contraction on the raw spectra, and the epilogue writes Y / M for every bin instead of accumulating |Y|^2 over bins.
-template <int NKC, bool FAN>   // K chunks per bin = 2M / 32 = M / 16
+template <int NKC>   // K chunks per bin = 2M / 32 = M / 16
 __global__ void __launch_bounds__(TC_THREADS, 1) srp_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                                                                 const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -333,36 +247,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) srp_tc_kernel(const __grid_cons
       const int ks = item / (p.n_tt * p.n_dt), tt = (item / p.n_dt) % p.n_tt, dt = item % p.n_dt;
       const int k_begin = ks * p.bins_per_range, k_end = min(p.K, k_begin + p.bins_per_range);
       const long long t = (long long)tt * TC_BM + quarter * 32 + lane;
-      if constexpr (FAN) {
-        const int d0 = dt * TC_BD + half * HD;
-        float2 *row = p.beams + (t * p.D + d0) * p.KP;   // direction d0 of frame t; only dereferenced when t < BT and d < D
-        for (int k = k_begin; k < k_end; ++k) {
-          mbar_wait_bounded(&tmem_full[acc], acc_phase);
-          tc_fence_after();
-          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + half * HD);
-#pragma unroll
-          for (int j = 0; j < HD / 16; ++j) {
-            float vr[16], vi[16];
-            tmem_ld16(taddr + j * 16, vr);
-            tmem_ld16(taddr + TC_BD + j * 16, vi);
-            if (t < p.BT) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int dd = j * 16 + i;
-                if (d0 + dd < p.D) {
-                  float2 *o = row + (size_t)dd * p.KP + k;
-                  *o = make_float2(vr[i] * p.out_scale, vi[i] * p.out_scale);
-                  if (k == p.K - 1) o[1] = make_float2(0.f, 0.f);   // the pad bin of the row
-                }
-              }
-            }
-          }
-          tc_fence_before();
-          mbar_arrive(&tmem_empty[acc]);
-          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        }
-        continue;
-      }
       float sum[HD];
 #pragma unroll
       for (int i = 0; i < HD; ++i) sum[i] = 0.f;
@@ -667,21 +551,6 @@ static int ts_launch(const float2 *spec, long long BT, int N, const uint64_t *mi
   return 0;
 }
 
-// cuTensorMapEncodeTiled is a driver entry point: fetched through the runtime so the library does not link libcuda.so
-// (it must still load, and fail loudly at mcag_create, on a box without a GPU driver).
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
-                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void *ptr = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  return fn;
-}
-
 static int encode_map(CUtensorMap *map, const float *base, long long BTpad, int M, int K) {
   EncodeTiledFn cuTensorMapEncodeTiled = encode_tiled_fn();
   if (!cuTensorMapEncodeTiled) return mcag_set_error(2, "cuTensorMapEncodeTiled is not available from this driver");
@@ -694,8 +563,8 @@ static int encode_map(CUtensorMap *map, const float *base, long long BTpad, int 
   return 0;
 }
 
-template <int NKC, bool FAN = false> static void launch_tc(int grid, cudaStream_t st, const CUtensorMap &hi, const CUtensorMap &lo, const TcParams &p) {
-  auto kern = srp_tc_kernel<NKC, FAN>;
+template <int NKC> static void launch_tc(int grid, cudaStream_t st, const CUtensorMap &hi, const CUtensorMap &lo, const TcParams &p) {
+  auto kern = srp_tc_kernel<NKC>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
   kern<<<grid, TC_THREADS, TC_SMEM, st>>>(hi, lo, p);
 }
@@ -748,7 +617,7 @@ int k_srp_tensor_ws(const float2 *spec, int B, int T, int M, int N, const uint64
   float *Uhi = reinterpret_cast<float *>(w), *Ulo = reinterpret_cast<float *>(w + u_bytes), *partial = reinterpret_cast<float *>(w + 2 * u_bytes),
         *nzsum = reinterpret_cast<float *>(w + 2 * u_bytes + part_bytes);
   p.partial = partial;
-  srp_prepare_kernel<true><<<(unsigned)BTpad, 256, 0, st>>>(spec, BT, BTpad, M, N, Uhi, Ulo, nzsum);
+  srp_prepare_kernel<<<(unsigned)BTpad, 256, 0, st>>>(spec, BT, BTpad, M, N, Uhi, Ulo, nzsum);
   MCAG_CHECK_LAUNCH();
   CUtensorMap map_hi, map_lo;
   OK_RC(encode_map(&map_hi, Uhi, BTpad, M, K));
@@ -769,58 +638,6 @@ int k_srp_tensor_ws(const float2 *spec, int B, int T, int M, int N, const uint64
   srp_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, p.n_ks, BT, D, nzsum, srp);
   MCAG_CHECK_LAUNCH();
   return 0;
-}
-
-// ---- delay-and-sum fan on the same kernel -----------------------------------------------------------------------------------
-// scratch: [X_hi | X_lo], each 1 KB aligned
-size_t k_ds_fan_tensor_workspace_bytes(long long BT, int M, int N) {
-  if (!k_srp_tensor_supported(M) || BT <= 0) return 0;
-  const long long BTpad = (BT + TC_BM - 1) / TC_BM * TC_BM;
-  auto al = [](size_t n) { return (n + 1023) & ~(size_t)1023; };
-  return 2 * al((size_t)(N / 2 + 1) * BTpad * 2 * M * 4);
-}
-int k_ds_fan_tensor_ws(const float2 *spec, int B, int T, int M, int N, const uint64_t *steer_fx, int D, float2 *out, void *workspace, size_t ws_bytes,
-                       cudaStream_t st) {
-  if (B <= 0 || T <= 0) return 0;
-  if (!k_srp_tensor_supported(M)) return k_ds_fan(spec, B, T, M, N, steer_fx, D, out, st);
-  const long long BT = (long long)B * T;
-  TcParams p; long long BTpad;
-  tc_plan(BT, M, N, D, p, BTpad);
-  p.mic_fx = steer_fx; p.partial = nullptr; p.beams = out; p.KP = spec_pitch(N); p.out_scale = 1.0f / (float)M;
-  const int K = p.K;
-  auto al = [](size_t n) { return (n + 1023) & ~(size_t)1023; };
-  const size_t u_bytes = al((size_t)K * BTpad * 2 * M * sizeof(float));
-  if (2 * u_bytes > ws_bytes) return mcag_set_error(4, "ds_fan_tensor: workspace too small");
-  unsigned char *w = static_cast<unsigned char *>(workspace);
-  float *Xhi = reinterpret_cast<float *>(w), *Xlo = reinterpret_cast<float *>(w + u_bytes);
-  srp_prepare_kernel<false><<<(unsigned)BTpad, 256, 0, st>>>(spec, BT, BTpad, M, N, Xhi, Xlo, nullptr);
-  MCAG_CHECK_LAUNCH();
-  CUtensorMap map_hi, map_lo;
-  OK_RC(encode_map(&map_hi, Xhi, BTpad, M, K));
-  OK_RC(encode_map(&map_lo, Xlo, BTpad, M, K));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long items = (long long)p.n_tt * p.n_dt * p.n_ks;
-  const int grid = (int)(items < sms ? items : sms);
-  switch (M / 16) {
-    case 1: launch_tc<1, true>(grid, st, map_hi, map_lo, p); break;
-    case 2: launch_tc<2, true>(grid, st, map_hi, map_lo, p); break;
-    case 3: launch_tc<3, true>(grid, st, map_hi, map_lo, p); break;
-    default: launch_tc<4, true>(grid, st, map_hi, map_lo, p); break;
-  }
-  MCAG_CHECK_LAUNCH();
-  return 0;
-}
-int k_ds_fan_tensor(const float2 *spec, int B, int T, int M, int N, const uint64_t *steer_fx, int D, float2 *out, cudaStream_t st) {
-  if (B <= 0 || T <= 0) return 0;
-  if (!k_srp_tensor_supported(M)) return k_ds_fan(spec, B, T, M, N, steer_fx, D, out, st);
-  const size_t bytes = k_ds_fan_tensor_workspace_bytes((long long)B * T, M, N);
-  void *ws = nullptr;
-  if (cudaMallocAsync(&ws, bytes, st) != cudaSuccess) return mcag_set_cuda_error(cudaGetLastError());
-  const int rc = k_ds_fan_tensor_ws(spec, B, T, M, N, steer_fx, D, out, ws, bytes, st);
-  cudaFreeAsync(ws, st);
-  return rc;
 }
 
 // kernel-level entry without a caller-owned workspace: stream-ordered scratch from the device's memory pool
@@ -844,9 +661,6 @@ int k_srp_tensor(const float2 *spec, int B, int T, int M, int N, const uint64_t 
 
 }  // namespace mcag
 
-extern "C" int mcag_k_ds_fan_tensor(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_steer_fx, int D, void *d_out, void *stream) {
-  return mcag::k_ds_fan_tensor((const float2 *)d_spec, B, T, M, N, d_steer_fx, D, (float2 *)d_out, (cudaStream_t)stream);
-}
 extern "C" int mcag_k_srp_tensor(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_mic_fx, int D, float *d_srp, void *stream) {
   return mcag::k_srp_tensor((const float2 *)d_spec, B, T, M, N, d_mic_fx, D, d_srp, (cudaStream_t)stream);
 }

@@ -302,13 +302,16 @@ class MultibandBinarualLocalisation(Processor):
 
 class FastBinauralMasking(Processor):
     def __init__(self, samplerate, microDistance, lowFreq, highFreq, mmethod="RELATIVE", algorithm="BOTH", n_streams=1,
-                 max_frames_per_call=256, frame_size=None, n_bands=45):
+                 max_frames_per_call=256, frame_size=None, n_bands=45, emit_spectra=False, emit_trace=False):
+        """emit_spectra keeps the analysis / masked spectra fetchable (staged kernels); emit_trace keeps Q() / decisions() of the last call.
+        Without them the whole chain is one fused kernel and only the audio (and the frame powers) come back."""
         N = frame_size or capi.frame_size(samplerate, 0.050)                # FastBinauralMasking.h:112
         H, fc, thr = capi.mel_bank(N, n_bands, samplerate, lowFreq, highFreq, microDistance)
         m = MaskingMethod[mmethod] if isinstance(mmethod, str) else mmethod
         a = MaskingAlg[algorithm] if isinstance(algorithm, str) else algorithm
         super().__init__(kind=capi.KIND_MASK, sample_rate=samplerate, frame_size=N, hop=N // 2, n_channels=2, n_streams=n_streams,
-                         max_frames_per_call=max_frames_per_call, mask_method=m, mask_alg=a, n_bands=n_bands, band_coefs=H, band_thresholds=thr)
+                         max_frames_per_call=max_frames_per_call, mask_method=m, mask_alg=a, n_bands=n_bands, band_coefs=H, band_thresholds=thr,
+                         emit=(capi.EMIT_SPECTRA if emit_spectra else 0) | (capi.EMIT_MASK_TRACE if emit_trace else 0))
         self.H, self.fc, self.thresholds = H, fc, thr
 
     def masked_spectra(self):

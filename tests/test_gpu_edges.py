@@ -62,7 +62,7 @@ def test_ragged_chunks_equal_one_shot(mb, kind):
         if kind == "ssl":
             return mb.SourceSeparationAndLocalisation(fs, xyz, 2, usePowerFloor=True, max_frames_per_call=32)
         if kind == "mask":
-            return mb.FastBinauralMasking(fs, 0.086, 500, 5000, "NOISY", "BOTH", max_frames_per_call=32, frame_size=512)
+            return mb.FastBinauralMasking(fs, 0.086, 500, 5000, "NOISY", "BOTH", max_frames_per_call=32, frame_size=512, emit_trace=True)
         if kind == "freqgcc":
             return mb.FreqGCCBinauralLocalisation(fs, 0.086, usePowerFloor=True, max_frames_per_call=32, frame_size=512, noise_preestimated=False)
         if kind == "multiband":

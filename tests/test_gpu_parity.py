@@ -363,7 +363,7 @@ def test_multiband_general_path_equals_fused_path(mb):
 def test_mask_against_reference_golden(mb, name, method):
     g = np.load(os.path.join(G, "mask_spatial_16k.npz"))
     x = g["x"].astype(np.float32)
-    p = mb.FastBinauralMasking(int(g["fs"]), float(g["mic_dist"]), float(g["lo"]), float(g["hi"]), method, "BOTH", max_frames_per_call=64)
+    p = mb.FastBinauralMasking(int(g["fs"]), float(g["mic_dist"]), float(g["lo"]), float(g["hi"]), method, "BOTH", max_frames_per_call=64, emit_trace=True)
     outs, Q = [], []
     for pos in range(0, x.shape[1], int(g["chunk"])):
         outs.append(p.process(x[:, pos:pos + int(g["chunk"])]))
@@ -382,15 +382,46 @@ def test_mask_decisions_vs_oracle(mb, orc):
     fs, d = 16000, 0.086
     xyz = scenes.linear_array([0, d])
     x = scenes.far_field_scene(xyz, fs, 20 * 1024, scenes.azimuth_dirs([0.0, np.deg2rad(60)]), seed=77).astype(np.float32)
-    p = mb.FastBinauralMasking(fs, d, 500, 5000, "RELATIVE", "BOTH", max_frames_per_call=64)
-    p.process(x)
-    dec, spec = p.decisions()[0], p.masked_spectra()[0]
+    # the fused kernel (default: spectra stay on chip, decisions kept on request) and the staged kernels (spectra fetchable)
+    p = mb.FastBinauralMasking(fs, d, 500, 5000, "RELATIVE", "BOTH", max_frames_per_call=64, emit_trace=True)
+    q = mb.FastBinauralMasking(fs, d, 500, 5000, "RELATIVE", "BOTH", max_frames_per_call=64, emit_spectra=True)
+    yp, yq = p.process(x), q.process(x)
     N = p.info.window_size
     S = orc.stft(x.astype(np.float64), N, N // 2)
     H, fc = orc.mel_bank(N, 45, fs, 500, 5000)
     ref_spec, ref_dec, _, _ = orc.mask_frames(S, N, fs, d, 1, 0, H, fc)
-    assert np.array_equal(dec.astype(np.int32), ref_dec), f"{np.sum(dec != ref_dec)} decisions differ"
-    assert_close(spec, ref_spec, (1, 2), "masked spectra")
+    for name, proc in (("fused", p), ("staged", q)):
+        dec = proc.decisions()[0]
+        assert np.array_equal(dec.astype(np.int32), ref_dec), f"{name}: {np.sum(dec != ref_dec)} decisions differ"
+    assert_close(q.masked_spectra()[0], ref_spec, (1, 2), "masked spectra")
+    with pytest.raises(Exception):
+        p.masked_spectra()                                             # the fused path never materialises them
+    hop = p.info.hop
+    assert_close(yp.T.reshape(-1, hop, 2), yq.T.reshape(-1, hop, 2), (1, 2), "fused vs staged audio")
+
+
+@pytest.mark.parametrize("N,method,alg", [(512, "NOISY", "BOTH"), (1024, "FACTOR", "TEMPORAL"), (2048, "FULL", "SPATIAL"), (512, "RELATIVE", "BOTH")])
+def test_mask_fused_kernel_equals_staged_kernels(mb, N, method, alg):
+    """mask_fused_kernel (analysis + mask + synthesis in one kernel) against the stft / stats / scan / apply / istft chain on several
+    streams fed in ragged chunks: same decisions and Q trace bit for bit, audio within tolerance, frame powers equal."""
+    fs, d, B = 16000, 0.086, 5
+    xyz = scenes.linear_array([0, d])
+    x = np.concatenate([scenes.far_field_scene(xyz, fs, 9 * N + 77, scenes.azimuth_dirs([0.0, np.deg2rad(20 + 15 * b)]), seed=300 + b) for b in range(B)]).astype(np.float32)
+    f = mb.FastBinauralMasking(fs, d, 500, 5000, method, alg, n_streams=B, max_frames_per_call=32, frame_size=N, emit_trace=True)
+    s = mb.FastBinauralMasking(fs, d, 500, 5000, method, alg, n_streams=B, max_frames_per_call=32, frame_size=N, emit_spectra=True)
+    pos = 0
+    for n in (N // 2 + 3, 3 * N, 5, 2 * N + 1, 10 ** 9):
+        a, b_ = f.process(x[:, pos:pos + n]), s.process(x[:, pos:pos + n])
+        pos += n
+        assert a.shape == b_.shape and f.frames_done == s.frames_done
+        if f.frames_done:
+            assert np.array_equal(f.decisions(), s.decisions())
+            assert np.array_equal(f.Q(), s.Q())
+            assert np.array_equal(f.power_db(), s.power_db())
+            hop = f.info.hop
+            assert_close(a.T.reshape(-1, hop, 2 * B), b_.T.reshape(-1, hop, 2 * B), (1, 2), f"fused vs staged audio N={N} {method}")
+        if pos >= x.shape[1]:
+            break
 
 
 # ---------------------------------------------------------------------------------------------------------------------
