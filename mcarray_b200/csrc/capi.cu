@@ -192,7 +192,8 @@ struct mcag_proc_s {
   DevBuf steer_fx, steer_tab, beams, tail[2], out_dev; int tail_cur = 0;
   DevBuf lags, curves, curve_state, fg, est, track_doa, track_prob;
   DevBuf mic_fx, srp_ws;
-  DevBuf H, H2, thr, stats, gains, Q, noise, dec, qtrace, band_lohi, bin_lohi;
+  DevBuf H, H2, thr, stats, gains, Q, noise, dec, qtrace, mask_tab;
+  int mask_n_h2c = 0, mask_n_hc = 0;
   bool mask_fused = false;   // MASK: analysis + mask + synthesis in one kernel (mask_fused.cu)
   DevBuf band_raw, band_energy, floor_pow, band_cells, mb_raw_cell, mb_raw_prob, mb_lohi;
   int mb_bw = 0, mb_kmin = 0, mb_kmax = 0; bool mb_fused = false;   // band supports (host copy of what mb_band_kernel derives from H)
@@ -466,21 +467,35 @@ int mcag_create(const mcag_config *cfg, mcag_proc *out) {
     }
     if ((rc = upload(p->H, H.data(), H.size() * 4, st)) || (rc = upload(p->H2, H2.data(), H2.size() * 4, st)) || (rc = upload(p->thr, thr.data(), nb * 4, st)))
       return fail(rc);
-    // band supports [lo, hi) per band and covering bands [lo, hi) per bin, as mask_stats_kernel / mask_apply_kernel derive them
-    std::vector<int> blh(2 * nb);
-    std::vector<unsigned char> klh(2 * (size_t)p->K);
-    for (size_t b = 0; b < nb; ++b) {
-      int lo = p->K, hi = 0;
-      for (int k = 0; k < p->K; ++k) if (H2[b * KP + k] != 0.f) { lo = std::min(lo, k); hi = k + 1; }
-      blh[2 * b] = lo; blh[2 * b + 1] = hi;
+    // compact tables of the fused kernel: band supports [lo, hi) with their squared magnitudes (band-major, what mask_stats_kernel sums)
+    // and, per bin, the covering bands [lo, hi) with their magnitudes at that bin (bin-major, what mask_apply_kernel sums)
+    if (p->mask_fused) {
+      std::vector<int> tab(4 * nb + p->K);
+      std::vector<float> h2c, hc;
+      for (size_t b = 0; b < nb; ++b) {
+        int lo = p->K, hi = 0;
+        for (int k = 0; k < p->K; ++k) if (H2[b * KP + k] != 0.f) { lo = std::min(lo, k); hi = k + 1; }
+        if (hi <= lo) { lo = 0; hi = 0; }
+        tab[4 * b] = lo; tab[4 * b + 1] = hi; tab[4 * b + 2] = (int)h2c.size(); tab[4 * b + 3] = 0;
+        for (int k = lo; k < hi; ++k) h2c.push_back(H2[b * KP + k]);
+      }
+      for (int k = 0; k < p->K; ++k) {
+        int lo = (int)nb, hi = 0;
+        for (size_t b = 0; b < nb; ++b) if (H[b * KP + k] != 0.f) { lo = std::min(lo, (int)b); hi = (int)b + 1; }
+        if (hi <= lo) { lo = 0; hi = 0; }
+        tab[4 * nb + k] = lo | (hi << 8) | ((int)hc.size() << 16);
+        for (int b = lo; b < hi; ++b) hc.push_back(H[(size_t)b * KP + k]);
+      }
+      if (nb > 255 || h2c.size() > 8192 || hc.size() > 8192) p->mask_fused = false;   // a dense bank: the staged kernels
+      else {
+        p->mask_n_h2c = (int)h2c.size(); p->mask_n_hc = (int)hc.size();
+        const size_t n0 = tab.size();
+        tab.resize(n0 + h2c.size() + hc.size());
+        std::memcpy(tab.data() + n0, h2c.data(), h2c.size() * 4);
+        std::memcpy(tab.data() + n0 + h2c.size(), hc.data(), hc.size() * 4);
+        if ((rc = upload(p->mask_tab, tab.data(), tab.size() * 4, st))) return fail(rc);
+      }
     }
-    for (int k = 0; k < p->K; ++k) {
-      int lo = (int)nb, hi = 0;
-      for (size_t b = 0; b < nb; ++b) if (H[b * KP + k] != 0.f) { lo = std::min(lo, (int)b); hi = (int)b + 1; }
-      klh[2 * k] = (unsigned char)lo; klh[2 * k + 1] = (unsigned char)hi;
-    }
-    if (nb > 255) p->mask_fused = false;
-    if ((rc = upload(p->band_lohi, blh.data(), blh.size() * sizeof(int), st)) || (rc = upload(p->bin_lohi, klh.data(), klh.size(), st))) return fail(rc);
     CUF(cudaStreamSynchronize(st));
     if ((rc = p->Q.alloc(4 * B * nb)) || (rc = p->noise.alloc(4 * B * nb))) return fail(rc);
     if (!p->mask_fused)
@@ -504,7 +519,7 @@ void mcag_destroy(mcag_proc p) {
                    &p->active, &p->gate, &p->pair_fx, &p->corr, &p->esum, &p->energy, &p->energy_state, &p->raw_idx, &p->raw_prob, &p->cells,
                    &p->prob, &p->cell_state, &p->prob_state, &p->steer_fx, &p->steer_tab, &p->beams, &p->tail[0], &p->tail[1], &p->out_dev,
                    &p->lags, &p->curves, &p->curve_state, &p->fg, &p->est, &p->track_doa, &p->track_prob, &p->mic_fx, &p->srp_ws, &p->H, &p->H2, &p->thr, &p->stats, &p->gains, &p->Q,
-                   &p->noise, &p->dec, &p->qtrace, &p->band_lohi, &p->bin_lohi, &p->band_raw, &p->band_energy, &p->floor_pow, &p->band_cells, &p->mb_raw_cell, &p->mb_raw_prob, &p->mb_lohi};
+                   &p->noise, &p->dec, &p->qtrace, &p->mask_tab, &p->band_raw, &p->band_energy, &p->floor_pow, &p->band_cells, &p->mb_raw_cell, &p->mb_raw_prob, &p->mb_lohi};
   for (DevBuf *b : all) b->release();
   for (auto &r : p->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (cudaEvent_t e : p->prof_pool) cudaEventDestroy(e);
@@ -627,7 +642,7 @@ static int run_frames(mcag_proc p, const float *x_all, long long pitch, int T, i
       const int nb_ = p->cfg.n_bands;
       const long long ov = N - hop;
       float *outp = ext_out ? ext_out + o * ext_rows * ext_pitch : p->out_dev.as<float>() + o * 2 * T * hop;
-      OK(k_mask_fused(x, pitch, B, T, N, hop, win, tw, p->H.as<float>(), p->H2.as<float>(), p->band_lohi.as<int>(), p->bin_lohi.as<unsigned char>(), nb_,
+      OK(k_mask_fused(x, pitch, B, T, N, hop, win, tw, p->mask_tab.as<int>(), p->mask_n_h2c, p->mask_n_hc, nb_,
                       p->cfg.mask_method, p->cfg.mask_alg, p->thr.as<float>(), p->Q.as<float>() + o * nb_, p->noise.as<float>() + o * nb_,
                       (int)(p->frames_total > 2 ? 2 : p->frames_total), p->tail[p->tail_cur].as<float>() + o * 2 * ov,
                       p->tail[p->tail_cur ^ 1].as<float>() + o * 2 * ov, outp, ext_out ? ext_pitch : (long long)T * hop, ext_out ? ext_rows : 2, chan_pow,

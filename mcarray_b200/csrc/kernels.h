@@ -59,8 +59,9 @@ int k_mask_apply(float2 *spec, long long BT, int N, const float *H, int nb, cons
 
 // mask_fused.cu: analysis + FastBinauralMasking + synthesis in one kernel, spectra never leave the SM (hop = N/2, N >= 512)
 bool k_mask_fused_supported(int N, int hop, int nb);
-int k_mask_fused(const float *x, long long row_pitch, int B, int T, int N, int hop, const float *win, const float2 *tw, const float *H, const float *H2,
-                 const int *band_lohi, const unsigned char *bin_lohi, int nb, int method, int alg, const float *thresholds, float *Q, float *noise,
+// tab: compact filter-bank tables {binfo[nb][4], kinfo[K], h2c[n_h2c], hc[n_hc]} (see MfParams)
+int k_mask_fused(const float *x, long long row_pitch, int B, int T, int N, int hop, const float *win, const float2 *tw, const int *tab, int n_h2c, int n_hc,
+                 int nb, int method, int alg, const float *thresholds, float *Q, float *noise,
                  int first_call, const float *tail_in, float *tail_out, float *out, long long out_pitch, int out_rows, float *chan_pow,
                  unsigned char *decisions, float *q_trace, cudaStream_t st);
 

@@ -21,9 +21,12 @@ struct MfParams {
   int B, T, hop;
   const float *win;          // [N]
   const float2 *tw;          // fft tables of N
-  const float *H, *H2;       // [nb][KP] band magnitudes and their squares
-  const int *band_lohi;      // [nb][2] first / one-past-last non-zero bin of each band
-  const unsigned char *bin_lohi;   // [K][2] first / one-past-last band covering each bin
+  // compact filter-bank tables (built by mcag_create, copied to shared memory once per CTA), 4-byte words:
+  //   binfo[nb][4] = {lo, hi, off, -}: band b covers bins [lo, hi), its squared magnitudes are h2c[off + k - lo]
+  //   kinfo[K]     = lo | hi << 8 | off << 16: bin k is covered by bands [lo, hi), their magnitudes at k are hc[off + b - lo]
+  //   h2c[n_h2c], hc[n_hc]
+  const int *tab;
+  int n_h2c, n_hc;
   int nb, method, alg, first_call;
   const float *thresholds;   // [nb]
   float *Q, *noise;          // [B][nb] carried state
@@ -39,7 +42,7 @@ struct MfParams {
 
 // SPC streams per CTA; a stream = 2 groups (left, right) of TPF = N/16 threads
 template <int N, int SPC>
-__global__ void __launch_bounds__(SPC * 2 * (N / 16), 768 / (SPC * 2 * (N / 16))) mask_fused_kernel(const MfParams p) {
+__global__ void __launch_bounds__(SPC * 2 * (N / 16), 896 / (SPC * 2 * (N / 16))) mask_fused_kernel(const MfParams p) {
   constexpr int NC = N / 2, TPF = NC / 8, KP = spec_pitch(N), K = N / 2 + 1, NH = N / 2, NTS = 2 * TPF, WPF = (TPF + 31) / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char *smem = fft_align_smem(smem_raw, 8 * NC);
@@ -50,10 +53,16 @@ __global__ void __launch_bounds__(SPC * 2 * (N / 16), 768 / (SPC * 2 * (N / 16))
   float2 *s_X_all = s_w + NC;                                             // SPC * 2 * KP spectra
   float2 *s_g_all = s_X_all + (size_t)SPC * 2 * KP;                       // SPC * nb gains (gl, gr)
   float *s_red_all = reinterpret_cast<float *>(s_g_all + (size_t)SPC * p.nb);   // SPC * 2 * WPF Parseval partials
+  int *s_tab = reinterpret_cast<int *>(s_red_all + ((SPC * 2 * WPF + 3) & ~3));   // binfo, kinfo, h2c, hc (16-byte aligned: nb * SPC is padded below)
+  s_tab += (4 - ((SPC * p.nb * 2) & 3)) & 3;
+  const int4 *s_binfo = reinterpret_cast<const int4 *>(s_tab);
+  const int *s_kinfo = s_tab + 4 * p.nb;
+  const float *s_h2c = reinterpret_cast<const float *>(s_kinfo + K), *s_hc = s_h2c + p.n_h2c;
 
   const int tid = threadIdx.x;
   fft_load_tables<N>(s_tw, p.tw, tid, blockDim.x);
   for (int i = tid; i < NC; i += blockDim.x) s_w[i] = make_float2(p.win[2 * i], p.win[2 * i + 1]);
+  for (int i = tid; i < 4 * p.nb + K + p.n_h2c + p.n_hc; i += blockDim.x) s_tab[i] = p.tab[i];
   __syncthreads();
 
   const int sl = tid / NTS, ts = tid % NTS;          // stream slot of the CTA, thread of the stream
@@ -84,6 +93,8 @@ __global__ void __launch_bounds__(SPC * 2 * (N / 16), 768 / (SPC * 2 * (N / 16))
     noise_r[u] = bd < p.nb ? p.noise[(long long)b * p.nb + bd] : 0.f;
   }
   int first_call = p.first_call;
+  const int4 my_band = s_binfo[ts < p.nb ? ts : 0];   // {lo, hi, off} of the band this thread sums
+  const float my_thr = p.thresholds[ts < p.nb ? ts : 0];
 
   // raw samples of the current frame, n = j + r TPF pairs: v[4..7] of frame t are v[0..3] of frame t + 1 (hop = N/2), so a frame costs
   // hop new samples per channel; they are requested one frame ahead (nxt) and arrive under the transforms of the current frame
@@ -140,11 +151,11 @@ __global__ void __launch_bounds__(SPC * 2 * (N / 16), 768 / (SPC * 2 * (N / 16))
     for (int u = 0; u < MF_BPT; ++u) {
       const int bd = ts + u * NTS;
       if (bd < p.nb) {
-        const float *h = p.H2 + (size_t)bd * KP;
+        const float *h = s_h2c + my_band.z - my_band.x;
         float st[MS_NSTAT] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        const int hi = p.band_lohi[2 * bd + 1];
-        for (int k = p.band_lohi[2 * bd]; k < hi; ++k) {
-          const float w = __ldg(h + k);
+        const int hi = my_band.y;
+        for (int k = my_band.x; k < hi; ++k) {
+          const float w = h[k];
           const float2 l = s_X[k], r = s_X[KP + k];
           const float mx = 0.5f * l.x + 0.5f * r.x, my = 0.5f * l.y + 0.5f * r.y;
           const float q0 = mx * mx + my * my, q1 = r.x * l.x + r.y * l.y, q2 = l.x * l.x + l.y * l.y, q3 = r.x * r.x + r.y * r.y;
@@ -152,7 +163,7 @@ __global__ void __launch_bounds__(SPC * 2 * (N / 16), 768 / (SPC * 2 * (N / 16))
           if (k < NH) { st[0] = fmaf(w, q0, st[0]); st[4] = fmaf(w, q2, st[4]); st[5] = fmaf(w, q3, st[5]); }
         }
         float gl, gr;
-        const int dec = mask_band_step(st, N, p.method, p.alg, p.thresholds[bd], first_call, Qr[u], noise_r[u], gl, gr);
+        const int dec = mask_band_step(st, N, p.method, p.alg, my_thr, first_call, Qr[u], noise_r[u], gl, gr);
         s_g[bd] = make_float2(gl, gr);
         const long long o = ((long long)b * p.T + t) * p.nb + bd;
         if (p.decisions) p.decisions[o] = (unsigned char)dec;
@@ -166,11 +177,11 @@ __global__ void __launch_bounds__(SPC * 2 * (N / 16), 768 / (SPC * 2 * (N / 16))
     for (int k = j; k < KP; k += TPF) {
       float wgt = 0.f;
       if (k < K) {
-        const int bhi = p.bin_lohi[2 * k + 1];
-        for (int bd = p.bin_lohi[2 * k]; bd < bhi; ++bd) {
-          const float h = __ldg(p.H + (size_t)bd * KP + k);
+        const int info = s_kinfo[k], blo = info & 255, bhi = (info >> 8) & 255;
+        const float *hk = s_hc + (info >> 16) - blo;
+        for (int bd = blo; bd < bhi; ++bd) {
           const float2 gg = s_g[bd];
-          wgt = fmaf(h, (k < NH) ? (c ? gg.y : gg.x) : 1.f, wgt);
+          wgt = fmaf(hk[bd], (k < NH) ? (c ? gg.y : gg.x) : 1.f, wgt);
         }
       }
       const float2 xv = X[k];
@@ -219,9 +230,12 @@ template <int N> static int launch_mask_fused(const MfParams &p, cudaStream_t st
   constexpr int NC = N / 2, TPF = NC / 8, NTS = 2 * TPF;
   constexpr int SPC = (NTS >= 256) ? 1 : (NTS >= 128 ? 2 : (NTS >= 64 ? 2 : 4));
   const size_t smem = sizeof(float2) * ((size_t)SPC * 2 * fft_buf_len(NC) + fft_table_len(N) + NC + (size_t)SPC * 2 * spec_pitch(N) + (size_t)SPC * p.nb) +
-                      sizeof(float) * SPC * 2 * ((TPF + 31) / 32) + 8 * NC /* buffer alignment slack */;
+                      sizeof(float) * SPC * 2 * ((TPF + 31) / 32) + 4 * (4 * (size_t)p.nb + N / 2 + 1 + p.n_h2c + p.n_hc) + 64 + 8 * NC /* buffer alignment slack */;
   auto kern = mask_fused_kernel<N, SPC>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // all of the unified L1 / shared memory as shared memory: the driver's default carve-out fitted 4 CTAs of 27 KB per SM, the
+  // registers allow 7 (28 warps; 2048 streams of cfg1m then run as a single wave)
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   kern<<<(unsigned)((p.B + SPC - 1) / SPC), SPC * NTS, smem, st>>>(p);
   MCAG_CHECK_LAUNCH();
   return 0;
@@ -232,8 +246,8 @@ bool k_mask_fused_supported(int N, int hop, int nb) {
   return hop * 2 == N && N >= 512 && nb >= 1 && nb <= NTS;   // N = 256 packs two transforms per warp: staged path
 }
 
-int k_mask_fused(const float *x, long long row_pitch, int B, int T, int N, int hop, const float *win, const float2 *tw, const float *H, const float *H2,
-                 const int *band_lohi, const unsigned char *bin_lohi, int nb, int method, int alg, const float *thresholds, float *Q, float *noise,
+int k_mask_fused(const float *x, long long row_pitch, int B, int T, int N, int hop, const float *win, const float2 *tw, const int *tab, int n_h2c, int n_hc,
+                 int nb, int method, int alg, const float *thresholds, float *Q, float *noise,
                  int first_call, const float *tail_in, float *tail_out, float *out, long long out_pitch, int out_rows, float *chan_pow,
                  unsigned char *decisions, float *q_trace, cudaStream_t st) {
   if (B <= 0 || T <= 0) return 0;
@@ -241,8 +255,8 @@ int k_mask_fused(const float *x, long long row_pitch, int B, int T, int N, int h
   if ((row_pitch & 1) || (out_pitch & 1) || (reinterpret_cast<uintptr_t>(x) & 7) || (reinterpret_cast<uintptr_t>(out) & 7))
     return mcag_set_error(1, "mask_fused: sample rows must be 8-byte aligned");
   MfParams p;
-  p.x = x; p.row_pitch = row_pitch; p.B = B; p.T = T; p.hop = hop; p.win = win; p.tw = tw; p.H = H; p.H2 = H2; p.band_lohi = band_lohi;
-  p.bin_lohi = bin_lohi; p.nb = nb; p.method = method; p.alg = alg; p.first_call = first_call; p.thresholds = thresholds; p.Q = Q; p.noise = noise;
+  p.x = x; p.row_pitch = row_pitch; p.B = B; p.T = T; p.hop = hop; p.win = win; p.tw = tw; p.tab = tab; p.n_h2c = n_h2c;
+  p.n_hc = n_hc; p.nb = nb; p.method = method; p.alg = alg; p.first_call = first_call; p.thresholds = thresholds; p.Q = Q; p.noise = noise;
   p.tail_in = tail_in; p.tail_out = tail_out; p.out = out; p.out_pitch = out_pitch; p.out_rows = out_rows; p.chan_pow = chan_pow;
   p.decisions = decisions; p.q_trace = q_trace;
   switch (N) {
