@@ -1,5 +1,7 @@
 /* Facade classes and the masking enums of include/mcarray/ArrayModules.h:41-106 (src/mcarray/ArrayModules.cpp:30-89).
- * SoundLocalisation picks FreqGCCBinauralLocalisation for two microphones and the SRP localiser otherwise (the reference's
+ * SoundLocalisation picks FreqGCCBinauralLocalisation for two microphones (with the deterministic DOA tracker: the reference facade
+ * publishes the particle filter's estimate, the `#else` branch of BinauralLocalisation.cpp:501-504 is its deterministic counterpart)
+ * and the SRP localiser otherwise (the reference's
  * >2-microphone branch casts an unrelated type and hard-codes 512, ArrayModules.cpp:46-53: not reproduced);
  * BinauralMasking wraps FastBinauralMasking with the distance between the first two microphones (:77). */
 #ifndef MCARRAY_B200_ARRAYMODULES_H
@@ -64,7 +66,7 @@ int BinauralMasking::getFrameSize() const { return _impl->getFrameSize(); }
 SoundLocalisation::SoundLocalisation(int sampleRate, ArrayDescription microphonePositions, LocalisationCallback *callback) {
   const bool usePowerFloor = true;
   LocalisingProcessor *loc;
-  if (microphonePositions.size() == 2) loc = new FreqGCCBinauralLocalisation(sampleRate, microphonePositions, usePowerFloor);
+  if (microphonePositions.size() == 2) loc = new FreqGCCBinauralLocalisation(sampleRate, microphonePositions, usePowerFloor, 1, 256, 0, 0, true);
   else loc = new SourceLocalisation(sampleRate, microphonePositions, 1, usePowerFloor);
   if (callback != NULL) loc->setCallback(callback);
   _impl.reset(loc);

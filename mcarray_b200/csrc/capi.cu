@@ -340,7 +340,7 @@ int mcag_create(const mcag_config *cfg, mcag_proc *out) {
   // synthesis pass) or the shape is outside the fused kernel; MCAG_MASK_STAGED=1 forces the staged kernels (tests compare the two)
   p->mask_fused = kind == MCAG_KIND_MASK && !(cfg->emit & MCAG_EMIT_SPECTRA) && cfg->mask_method != 5 && k_mask_fused_supported(N, cfg->hop, cfg->n_bands) &&
                   !getenv("MCAG_MASK_STAGED");
-  if ((kind != MCAG_KIND_TDOA && !p->mask_fused) || (cfg->emit & MCAG_EMIT_SPECTRA))
+  if ((kind != MCAG_KIND_TDOA && !p->mask_fused) || (cfg->emit & MCAG_EMIT_SPECTRA) || (kind == MCAG_KIND_TDOA && !k_stft_tdoa_fits(p->M, N)))
     if ((rc = p->spec.alloc(sizeof(float2) * B * T * M * KP))) return fail(rc);
   if ((rc = p->chan_pow.alloc(sizeof(float) * B * T * M))) return fail(rc);
   if ((rc = p->power_db.alloc(sizeof(float) * B * T))) return fail(rc);

@@ -58,7 +58,7 @@ template <int N> __device__ __forceinline__ void load_eo_twiddles(const float2 *
 template <int N, int G>
 __device__ __forceinline__ void tdoa_pairs(const float2 *s_U, const float2 (&wk)[4], const float2 *s_twp, fft_buf_t buf, const unsigned char *s_pair,
                                            float *s_bv, int *s_bi, int P, int max_lag, int g, int j, float *__restrict__ curves_ft,
-                                           int32_t *__restrict__ lags_ft, float *__restrict__ peaks_ft) {
+                                           int32_t *__restrict__ lags_ft, float *__restrict__ peaks_ft, const int *s_pout = nullptr) {
   constexpr int NC = N / 2, TPF = NC / 8, KP = spec_pitch(N);
   using PL = FftPlan<NC>;
   constexpr int RL = PL::R[PL::NP - 1], NBL = 8 / RL, NSL = NC / RL;
@@ -97,7 +97,8 @@ __device__ __forceinline__ void tdoa_pairs(const float2 *s_U, const float2 (&wk)
     for (int r = 4; r < 8; ++r) v[r] = lds64(buf ^ (8u * (uint32_t)fft_pad(8 * j + r)));
     const float g0 = Ui[0].x * Uj[0].x, gny = Ui[NC].x * Uj[NC].x;   // both spectra are real at DC / Nyquist
     const float b_even = 0.5f * (g0 + gny), b_odd = 0.5f * (g0 - gny);
-    float *cdst = (curves_ft && live) ? curves_ft + (size_t)p * L : nullptr;
+    const int po = s_pout ? s_pout[pc] : p;   // where the pair's results go (channel-tiled launches: the global pair index)
+    float *cdst = (curves_ft && live) ? curves_ft + (size_t)po * L : nullptr;
     float best = -3.0e38f; int besti = 0x7fffffff;
     auto cand = [&](int l, float val) {   // first maximum: the lowest window index wins ties
       const float sv = val + ((l & 1) ? b_odd : b_even);
@@ -152,8 +153,8 @@ __device__ __forceinline__ void tdoa_pairs(const float2 *s_U, const float2 (&wk)
       if (j == 0 && live) {
         unsigned bk = s_bk[g * WPF]; int bi = s_bx[g * WPF];
         for (int w = 1; w < WPF; ++w) { unsigned ok = s_bk[g * WPF + w]; int oi = s_bx[g * WPF + w]; if (ok > bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; } }
-        lags_ft[p] = bi - max_lag;
-        if (peaks_ft) peaks_ft[p] = float_from_order_key(bk);
+        lags_ft[po] = bi - max_lag;
+        if (peaks_ft) peaks_ft[po] = float_from_order_key(bk);
       }
     } else {
       const unsigned gmask = ((1u << (TPF & 31)) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(TPF - 1));
@@ -164,45 +165,59 @@ __device__ __forceinline__ void tdoa_pairs(const float2 *s_U, const float2 (&wk)
         if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
       }
       if (j == 0 && live) {
-        lags_ft[p] = besti - max_lag;
-        if (peaks_ft) peaks_ft[p] = best;
+        lags_ft[po] = besti - max_lag;
+        if (peaks_ft) peaks_ft[po] = best;
       }
       group_sync<TPF>(g);
     }
   }
 }
 
+// Channel tiles: the kernel stages the whitened spectra of channels [ci0, ci0 + cin) and, when cjn > 0, [cj0, cj0 + cjn) and runs the
+// pairs (i < j) inside the first tile (cjn = 0) or every (i in the first, j in the second) pair; results land at the pair's global
+// index i (2M - i - 1)/2 + j - i - 1.  One launch with cin = M covers arrays whose spectra fit in shared memory; larger arrays (64
+// microphones at N = 1024 need 263 KB) are covered tile pair by tile pair.
 template <int N, int G>
 __global__ void __launch_bounds__(G *(N / 16)) tdoa_kernel(const float2 *__restrict__ spec, int T, int M, int max_lag,
                                                             const float2 *__restrict__ tw_g, float *__restrict__ curves,
-                                                            int32_t *__restrict__ lags, float *__restrict__ peaks) {
+                                                            int32_t *__restrict__ lags, float *__restrict__ peaks, int ci0, int cin, int cj0, int cjn) {
   constexpr int NC = N / 2, TPF = NC / 8, KP = spec_pitch(N), NT = G * TPF, WPF = (TPF + 31) / 32;
   const int P = M * (M - 1) / 2, L = 2 * max_lag + 1;
+  const int CS = cin + cjn, PL = cjn ? cin * cjn : cin * (cin - 1) / 2;   // staged channels, pairs of this launch
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned char *smem = fft_align_smem(smem_raw, 8 * NC);
   float2 *s_buf = reinterpret_cast<float2 *>(smem);                   // G * fft_buf_len(NC), each buffer aligned to its size
-  float2 *s_U = s_buf + G * fft_buf_len(NC);                          // M * KP
-  float2 *s_tw = s_U + (size_t)M * KP;                                // fft_table_len(N): tw[NC] then twp
+  float2 *s_U = s_buf + G * fft_buf_len(NC);                          // CS * KP
+  float2 *s_tw = s_U + (size_t)CS * KP;                               // fft_table_len(N): tw[NC] then twp
   float2 *s_twp = s_tw + NC;
   float *s_bv = reinterpret_cast<float *>(s_tw + fft_table_len(N));   // 2 * G * WPF (double-buffered by pair round)
   int *s_bi = reinterpret_cast<int *>(s_bv + 2 * G * WPF);            // 2 * G * WPF
-  unsigned char *s_pair = reinterpret_cast<unsigned char *>(s_bi + 2 * G * WPF);   // 2 * P
+  int *s_pout = s_bi + 2 * G * WPF;                                   // PL global pair indices
+  unsigned char *s_pair = reinterpret_cast<unsigned char *>(s_pout + PL);   // 2 * PL staged-slot pairs
 
   const int tid = threadIdx.x, t = blockIdx.x, b = blockIdx.y;
   const float2 *src = spec + ((long long)b * T + t) * M * KP;
-  for (int i = tid; i < M * KP; i += NT) {
-    const int k = i % KP;
-    s_U[i] = (k <= NC) ? whiten(src[i]) : make_float2(0.f, 0.f);
+  for (int i = tid; i < CS * KP; i += NT) {
+    const int slot = i / KP, k = i - slot * KP;
+    const int ch = slot < cin ? ci0 + slot : cj0 + (slot - cin);
+    s_U[i] = (k <= NC) ? whiten(src[(size_t)ch * KP + k]) : make_float2(0.f, 0.f);
   }
   fft_load_tables<N>(s_tw, tw_g, tid, NT);
-  pair_table<N, G>(s_pair, M, P, tid, NT);
+  for (int q = tid; q < PL; q += NT) {   // local pair q -> staged slots and global pair index, lexicographic like SteeringBeamforming.cpp:63-65
+    int a, c;
+    if (cjn) { a = q / cjn; c = cin + (q - a * cjn); }
+    else { a = 0; int rem = q; while (rem >= cin - 1 - a) { rem -= cin - 1 - a; ++a; } c = a + 1 + rem; }
+    const int gi = ci0 + a, gj = c < cin ? ci0 + c : cj0 + (c - cin);
+    s_pair[2 * q] = (unsigned char)a; s_pair[2 * q + 1] = (unsigned char)c;
+    s_pout[q] = gi * (2 * M - gi - 1) / 2 + (gj - gi - 1);
+  }
   __syncthreads();
   const int g = tid / TPF, j = tid % TPF;
   const long long ft = (long long)b * T + t;
   float2 wk[4];
   load_eo_twiddles<N>(s_tw, j, wk);
-  tdoa_pairs<N, G>(s_U, wk, s_twp, smem_u32(s_buf + g * fft_buf_len(NC)), s_pair, s_bv, s_bi, P, max_lag, g, j,
-                   curves ? curves + ft * P * L : nullptr, lags + ft * P, peaks ? peaks + ft * P : nullptr);
+  tdoa_pairs<N, G>(s_U, wk, s_twp, smem_u32(s_buf + g * fft_buf_len(NC)), s_pair, s_bv, s_bi, PL, max_lag, g, j,
+                   curves ? curves + ft * P * L : nullptr, lags + ft * P, peaks ? peaks + ft * P : nullptr, s_pout);
 }
 
 // Analysis phase of the fused kernels: the M windows of frame (b, t) are read straight from the sample rows (coalesced 8-byte loads, the
@@ -425,14 +440,36 @@ template <int N> static int launch_tdoa(const float2 *spec, int B, int T, int M,
                                         float *peaks, cudaStream_t st) {
   constexpr int NC = N / 2, TPF = NC / 8;
   constexpr int G = (TPF >= 128) ? 2 : (256 / TPF);
-  const int P = M * (M - 1) / 2, L = 2 * max_lag + 1;
-  size_t smem = sizeof(float2) * ((size_t)M * spec_pitch(N) + fft_table_len(N) + (size_t)G * fft_buf_len(NC)) +
-                16 * G * ((TPF + 31) / 32) + 2 * P + 16 + 8 * NC /* buffer alignment slack */;
-  if (smem > 220 * 1024) return mcag_set_error(1, "tdoa: M*N too large for the shared-memory staged kernel");
+  auto smem_for = [&](int cs, int pl) {
+    return sizeof(float2) * ((size_t)cs * spec_pitch(N) + fft_table_len(N) + (size_t)G * fft_buf_len(NC)) + 16 * G * ((TPF + 31) / 32) + 6 * (size_t)pl + 16 +
+           8 * NC /* buffer alignment slack */;
+  };
   auto kern = tdoa_kernel<N, G>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  kern<<<dim3(T, B), G * TPF, smem, st>>>(spec, T, M, max_lag, tw, curves, lags, peaks);
-  MCAG_CHECK_LAUNCH();
+  const size_t cap = 220 * 1024;
+  if (smem_for(M, M * (M - 1) / 2) <= cap) {
+    const size_t smem = smem_for(M, M * (M - 1) / 2);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<dim3(T, B), G * TPF, smem, st>>>(spec, T, M, max_lag, tw, curves, lags, peaks, 0, M, 0, 0);
+    MCAG_CHECK_LAUNCH();
+    return 0;
+  }
+  // channel tiles of C channels: 2 C spectra staged per launch
+  int C = M;
+  while (C > 1 && smem_for(2 * C, C * C) > cap) --C;
+  if (smem_for(2 * C, C * C) > cap) return mcag_set_error(1, "tdoa: frame size too large for the shared-memory staged kernel");
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(2 * C, C * C));
+  for (int i0 = 0; i0 < M; i0 += C) {
+    const int ni = (M - i0 < C) ? M - i0 : C;
+    if (ni > 1) {
+      kern<<<dim3(T, B), G * TPF, smem_for(ni, ni * (ni - 1) / 2), st>>>(spec, T, M, max_lag, tw, curves, lags, peaks, i0, ni, 0, 0);
+      MCAG_CHECK_LAUNCH();
+    }
+    for (int j0 = i0 + C; j0 < M; j0 += C) {
+      const int nj = (M - j0 < C) ? M - j0 : C;
+      kern<<<dim3(T, B), G * TPF, smem_for(ni + nj, ni * nj), st>>>(spec, T, M, max_lag, tw, curves, lags, peaks, i0, ni, j0, nj);
+      MCAG_CHECK_LAUNCH();
+    }
+  }
   return 0;
 }
 
@@ -443,7 +480,7 @@ template <int N> static int launch_stft_tdoa(const float *x, long long row_pitch
   const int P = M * (M - 1) / 2, L = 2 * max_lag + 1;
   size_t smem = sizeof(float2) * ((size_t)M * spec_pitch(N) + fft_table_len(N) + (size_t)G * fft_buf_len(NC) + NC) +
                 16 * G * ((TPF + 31) / 32) + 2 * P + 16 + 8 * NC /* buffer alignment slack */;
-  if (smem > 220 * 1024) return mcag_set_error(1, "tdoa: M*N too large for the shared-memory staged kernel");
+  if (smem > 220 * 1024) return -1;   // more spectra than one CTA can stage: the caller runs stft + the channel-tiled lag kernel
   auto kern = stft_tdoa_kernel<N, G>;
   static int sm_count = 0, dev_cached = -1;
   int dev = 0;
@@ -474,9 +511,21 @@ int k_tdoa_lags(const float2 *spec, int B, int T, int M, int N, int max_lag, con
   return mcag_set_error(1, "tdoa: frame size must be 256, 512, 1024 or 2048");
 }
 
+bool k_stft_tdoa_fits(int M, int N) {   // the fused kernel stages all M spectra of a frame in one CTA
+  const int NC = N / 2, TPF = NC / 8, G = (TPF >= 128) ? 4 : (256 / TPF);
+  return sizeof(float2) * ((size_t)M * spec_pitch(N) + fft_table_len(N) + (size_t)G * fft_buf_len(NC) + NC) + 16 * G * ((TPF + 31) / 32) + (size_t)M * (M - 1) + 16 +
+             8 * NC <= 220 * 1024;
+}
+
 int k_stft_tdoa(const float *x, long long row_pitch, int B, int T, int M, int N, int hop, int max_lag, const float *win, const float2 *tw,
                 float2 *spec, float *chan_pow, float *curves, int32_t *lags, cudaStream_t st) {
   if (T <= 0 || B <= 0) return 0;
+  if (!k_stft_tdoa_fits(M, N)) {   // large arrays: spectra through HBM (the caller provides `spec`), then the channel-tiled lag kernel
+    if (!spec) return mcag_set_error(1, "tdoa: this array needs a spectrum buffer (more channels than the fused kernel stages)");
+    const int rc = k_stft(x, row_pitch, B * M, M, T, N, hop, win, tw, spec, chan_pow, nullptr, st);
+    if (rc) return rc;
+    return k_tdoa_lags(spec, B, T, M, N, max_lag, tw, curves, lags, nullptr, st);
+  }
   if (M < 2 || M > 255) return mcag_set_error(1, "tdoa: need 2..255 channels");
   if (max_lag < 0 || max_lag > N / 2 - 1) return mcag_set_error(1, "tdoa: max_lag out of range");
   if (hop <= 0 || hop > N) return mcag_set_error(1, "tdoa: bad hop");

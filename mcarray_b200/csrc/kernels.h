@@ -15,6 +15,7 @@ int k_frame_power(const float2 *spec, long long rows, int N, float *pow, cudaStr
 // gcc.cu
 int k_tdoa_lags(const float2 *spec, int B, int T, int M, int N, int max_lag, const float2 *tw, float *curves, int32_t *lags, float *peaks,
                 cudaStream_t st);
+bool k_stft_tdoa_fits(int M, int N);   // false: k_stft_tdoa needs `spec` and runs stft + the channel-tiled lag kernel
 int k_stft_tdoa(const float *x, long long row_pitch, int B, int T, int M, int N, int hop, int max_lag, const float *win, const float2 *tw,
                 float2 *spec, float *chan_pow, float *curves, int32_t *lags, cudaStream_t st);
 int k_gcc_tau(const float2 *spec, int B, int T, int M, int N, const uint64_t *pair_fx, int D, float *corr, cudaStream_t st);

@@ -4,6 +4,10 @@
 //        runs mca::SourceSeparationAndLocalisation through process(std::vector<double*>&, ...) in `chunk`-sample calls the
 //        way mcabeamf.cpp:101-119 does, and the frame-level mca::BeamformingSeparationAndLocalisation on the same spectra is
 //        left to the Python parity tests; writes <out_prefix>.doa (text, one callback per line) and <out_prefix>.out (f64).
+//   test_mcarray_api facade <in.s16> <n> <fs> <dist> <chunk> <out_prefix>
+//        the ArrayModules facades (include/mcarray/ArrayModules.h:41-106): mca::SoundLocalisation (2 microphones ->
+//        FreqGCCBinauralLocalisation, usePowerFloor = true, deterministic DOA tracker) and mca::BinauralMasking (FastBinauralMasking,
+//        500-5000 Hz, RELATIVE / BOTH) fed int16 PCM in `chunk`-sample calls; writes <out_prefix>.doa and <out_prefix>.out (s16, planar).
 //   test_mcarray_api frame <fs> <N>           -> SteeringBeamforming / Beamformer / BSAL frame-level classes on a synthetic
 //        plane wave: the selected DOA must be the source cell and the beamformer steered there must return the source.
 #include <mcarray/micarray.h>
@@ -129,6 +133,39 @@ static int runMultiband(int argc, char **argv) {
   return g_failures ? 1 : 0;
 }
 
+// the two facade classes of ArrayModules.h on a planar int16 stereo signal
+static int runFacade(int argc, char **argv) {
+  if (argc < 8) return 64;
+  const int n = std::atoi(argv[3]), fs = std::atoi(argv[4]), chunk = std::atoi(argv[6]);
+  const double dist = std::atof(argv[5]);
+  std::vector<int16_t> x(size_t(2) * n);
+  std::ifstream f(argv[2], std::ios::binary);
+  f.read(reinterpret_cast<char *>(x.data()), std::streamsize(x.size() * 2));
+  if (!f) { std::cerr << "short read" << std::endl; return 65; }
+  ArrayDescription array = ArrayDescription::make_linear_array_description(std::vector<double>{0.0, dist});
+  std::ofstream doa(std::string(argv[7]) + ".doa");
+  RecordingCallback cb(doa);
+  SoundLocalisation loc(fs, array, &cb);
+  BinauralMasking mask(fs, array, 500, 5000, BinauralMasking::RELATIVE, BinauralMasking::BOTH);
+  EXPECT(loc.getFrameSize() > 0 && mask.getFrameSize() > 0);
+  const int cap = chunk + mask.getMaxLatency();
+  std::vector<int16_t> o0(cap), o1(cap);
+  std::vector<int16_t *> rin(2), rout{o0.data(), o1.data()};
+  std::vector<int16_t> y0, y1;
+  for (int pos = 0; pos < n; pos += chunk) {
+    const int m = std::min(chunk, n - pos);
+    for (int c = 0; c < 2; ++c) rin[c] = x.data() + size_t(c) * n + pos;
+    loc.process(rin, m);
+    const int got = mask.process(rin, m, rout, cap);
+    y0.insert(y0.end(), o0.begin(), o0.begin() + got); y1.insert(y1.end(), o1.begin(), o1.begin() + got);
+  }
+  std::ofstream audio(std::string(argv[7]) + ".out", std::ios::binary);
+  audio.write(reinterpret_cast<const char *>(y0.data()), std::streamsize(y0.size() * 2));
+  audio.write(reinterpret_cast<const char *>(y1.data()), std::streamsize(y1.size() * 2));
+  std::cout << "frames with callbacks: " << cb.count << ", samples out: " << y0.size() << std::endl;
+  return g_failures ? 1 : 0;
+}
+
 // plane wave from grid cell `cell` on a linear array: X_c[k] = S[k] exp(+j 2 pi k fs/N x_c sin(theta)/c)
 static int runFrame(int argc, char **argv) {
   const int fs = argc > 2 ? std::atoi(argv[2]) : 16000, N = argc > 3 ? std::atoi(argv[3]) : 512, ccs = N + 2, K = N / 2 + 1;
@@ -178,6 +215,7 @@ int main(int argc, char **argv) {
     if (mode == "ssl") return runSsl(argc, argv);
     if (mode == "frame") return runFrame(argc, argv);
     if (mode == "multiband") return runMultiband(argc, argv);
+    if (mode == "facade") return runFacade(argc, argv);
   } catch (const std::exception &e) {
     std::cerr << "exception: " << e.what() << std::endl;
     return 3;

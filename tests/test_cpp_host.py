@@ -109,6 +109,46 @@ def test_cpp_multiband_against_reference_golden(tools, tmp_path):
 
 
 @pytest.mark.gpu
+def test_cpp_facades_against_oracle_and_golden(tools, tmp_path, orc):
+    """mca::SoundLocalisation and mca::BinauralMasking (ArrayModules.h:41-106) over int16 PCM: the localiser's callbacks carry the
+    deterministic tracker's DOA (bit-exact against the oracle, usePowerFloor = true with the floor estimated from a quiet lead-in), the
+    masker reproduces the reference fixture of the spatial-masking test signal."""
+    from mcarray_b200 import scenes
+    fs, d = 16000, 0.086
+
+    def run(x, tag):
+        x.astype(np.int16).tofile(tmp_path / f"{tag}.s16")
+        r = subprocess.run([os.path.join(tools, "test_mcarray_api"), "facade", str(tmp_path / f"{tag}.s16"), str(x.shape[1]), str(fs), repr(d), "3000",
+                            str(tmp_path / tag)], capture_output=True, text=True, timeout=180)
+        assert r.returncode == 0, r.stdout + r.stderr
+        doa = open(tmp_path / f"{tag}.doa").read()
+        rows = np.array([[float(v) for v in ln.split()] for ln in doa.split("\n") if ln.strip()]).reshape(-1, 3)
+        return rows, np.fromfile(tmp_path / f"{tag}.out", dtype=np.int16).reshape(2, -1)
+
+    # (1) masking: the reference's spatial-masking test signal (test_mcarray.cpp:908-929) against the fixture made by the reference build
+    g = np.load(os.path.join(G, "mask_spatial_16k.npz"))
+    _, y = run(g["x"].astype(np.float64), "mask")
+    ref = g["out_relative"]
+    assert y.shape == ref.shape
+    assert np.max(np.abs(y - ref)) <= 1.0 + 1e-4 * np.max(np.abs(ref))                 # int16 rounding of the output
+    # (2) localisation: quiet lead-in (the 3 s noise-floor estimate), then a source at +33 degrees; every delivery is an above-floor
+    #     frame of the oracle and carries the deterministic tracker's DOA in degrees
+    rng = np.random.default_rng(5)
+    lead = np.round(rng.standard_normal((2, 3 * fs + 4096)) * 3.0)
+    voiced = np.round(scenes.far_field_scene(scenes.linear_array([0, d]), fs, 12 * 1024, scenes.azimuth_dirs([np.deg2rad(33)]), seed=21))
+    x = np.concatenate([lead, voiced], axis=1)
+    rows, _ = run(x, "loc")
+    t = orc.freqgcc_track_run(fs, d, x, chunk=3000, use_floor=True, noise_preestimated=False)
+    act = t["active"].astype(bool)
+    assert rows.shape[0] == act.sum() > 5
+    assert np.array_equal(rows[:, 0], np.degrees(t["doa_rad"][act]))
+    near_cut = np.abs(t["prob"][act] - 0.01) < 1e-4
+    assert np.allclose(rows[~near_cut, 1], t["prob"][act][~near_cut], rtol=1e-3, atol=1e-5)
+    assert np.allclose(rows[:, 2], t["power"][act], atol=1e-3)
+    assert abs(rows[-1, 0] - 33) < 3.1                                                 # the tracker has settled on the source's cell
+
+
+@pytest.mark.gpu
 def test_mcbeam_cli_against_reference_golden(tools, tmp_path):
     """mcbeam -i in.wav -o out.wav -d doa.txt on the reference CLI's own hard-coded array (mcabeamf.cpp:182)."""
     g = np.load(os.path.join(G, "ssl_mcbeam_48k.npz"))
