@@ -129,6 +129,10 @@ typedef struct {
    * 3 s of silence; BinauralLocalisation.cpp:502-504,523-524,528-561) and setProbability (:569-631).  0 = off (arg-max cell only). */
   int doa_tracker;
   float doa_memory;       /* 0.6f: _maxDoaMemoryFactor, BinauralLocalisation.h:199 */
+
+  /* DSFAN as a filter-and-sum beamformer: per-bin complex weights [D][M][N/2+1] (re, im interleaved) used instead of the delay phasors
+   * of steer_turns, Y[d][k] = 1/M sum_c X_c[k] W[d][c][k].  NULL = delay-and-sum (Beamformer.cpp:51-71). */
+  const double *fs_weights;
 } mcag_config;
 
 typedef struct {
@@ -215,6 +219,8 @@ int mcag_k_select_doa(const float *d_energy, long long BT, int D, int n_pairs, i
  * ordered(E) << 31 | (0x7FFFFFFF - d): an int64 MAX all-reduce over the slices of a sharded grid gives the global arg-max cell */
 int mcag_k_argmax_pack(const float *d_map, long long rows, int D, int d_offset, long long *d_packed, void *stream);
 int mcag_k_ds_fan(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_steer_fx, int D, void *d_out, void *stream);
+/* filter-and-sum: the same fan with loaded weights d_weights float2 [D][M][N/2+2] instead of generated delay phasors */
+int mcag_k_fs_fan(const void *d_spec, int B, int T, int M, int N, const void *d_weights, int D, void *d_out, void *stream);
 /* the fan on the tensor cores (tcgen05, 3xTF32; M in {16, 32, 48, 64}, other counts run mcag_k_ds_fan): four consecutive bins of a
  * (128-frame, 64-direction) tile stay resident in TMEM, so every (frame, direction) leaves as 32 contiguous bytes of its [B][T][D][K] row.
  * What MCAG_KIND_DSFAN runs for those microphone counts.  The pad bin of d_spec rows must be zero (it is, for spectra of this library). */

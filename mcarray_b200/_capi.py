@@ -24,7 +24,7 @@ class Config(C.Structure):
         ("energy_memory", C.c_float), ("corr_memory", C.c_float), ("use_power_floor", C.c_int), ("noise_margin_db", C.c_float),
         ("floor_seconds", C.c_float), ("floor_ccs_power", C.c_int), ("noise_preestimated", C.c_int), ("max_lag", C.c_int),
         ("mask_method", C.c_int), ("mask_alg", C.c_int), ("n_bands", C.c_int), ("band_coefs", c_dp), ("band_thresholds", c_dp),
-        ("srp_form", C.c_int), ("doa_tracker", C.c_int), ("doa_memory", C.c_float),
+        ("srp_form", C.c_int), ("doa_tracker", C.c_int), ("doa_memory", C.c_float), ("fs_weights", c_dp),
     ]
 
 

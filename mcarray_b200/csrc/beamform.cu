@@ -61,9 +61,13 @@ int k_ds_select(const float2 *spec, int B, int T, int M, int N, const float2 *st
 // accumulators): per microphone the 4 steering phasors are generated once (32-bit fixed-point phase, exact wrap, MUFU sin / cos)
 // and reused for the 8 frames, the 8 spectrum values are read once and reused for the 4 directions.  Channels are added in
 // index order like Beamformer.cpp:56-68.  Output rows are written 256 bytes at a time (32 consecutive bins).
+// LOADED = true is the filter-and-sum beamformer: the per-bin complex weights W[d][c][k] come from memory instead of being generated as
+// delay phasors, Y[t][d][k] = (1/M) sum_c X_c[t][k] W[d][c][k] (same channel order, same 1/M): with W = exp(j k phi_c(d)) it IS the
+// delay-and-sum fan.  The reference has no filter-and-sum class; BASELINE.json's north_star names it next to delay-and-sum.
 constexpr int FAN_TF = 8, FAN_TD = 4, FAN_KC = 32;
+template <bool LOADED>
 __global__ void __launch_bounds__(256, 2) ds_fan_kernel(const float2 *__restrict__ spec, int T, int M, int N, const uint64_t *__restrict__ fx,
-                                                         int D, float2 *__restrict__ out) {
+                                                         const float2 *__restrict__ W, int D, float2 *__restrict__ out) {
   extern __shared__ float2 s_X[];   // [FAN_TF][M][FAN_KC]
   const int KP = spec_pitch(N), K = N / 2 + 1;
   const int t0 = blockIdx.x * FAN_TF, k0 = blockIdx.y * FAN_KC, b = blockIdx.z;
@@ -87,9 +91,13 @@ __global__ void __launch_bounds__(256, 2) ds_fan_kernel(const float2 *__restrict
       float2 a[FAN_TD];
 #pragma unroll
       for (int i = 0; i < FAN_TD; ++i) {
-        const uint64_t f64 = __ldg(fx + (size_t)min(d0 + i, D - 1) * M + c);
-        const int32_t ph = (int32_t)((uint32_t)((f64 + 0x80000000ull) >> 32) * (uint32_t)k);   // signed turns * 2^32, wraps exactly
-        __sincosf((float)ph * 1.4629180792671596e-09f, &a[i].y, &a[i].x);                      // 2 pi / 2^32
+        if constexpr (LOADED) {
+          a[i] = __ldg(W + ((size_t)min(d0 + i, D - 1) * M + c) * KP + k);                         // lanes = consecutive bins: 256-byte rows
+        } else {
+          const uint64_t f64 = __ldg(fx + (size_t)min(d0 + i, D - 1) * M + c);
+          const int32_t ph = (int32_t)((uint32_t)((f64 + 0x80000000ull) >> 32) * (uint32_t)k);   // signed turns * 2^32, wraps exactly
+          __sincosf((float)ph * 1.4629180792671596e-09f, &a[i].y, &a[i].x);                      // 2 pi / 2^32
+        }
       }
 #pragma unroll
       for (int f = 0; f < FAN_TF; ++f) {
@@ -117,9 +125,22 @@ int k_ds_fan(const float2 *spec, int B, int T, int M, int N, const uint64_t *ste
   const int KP = spec_pitch(N);
   size_t smem = sizeof(float2) * FAN_TF * M * FAN_KC;
   if (smem > 200 * 1024) return mcag_set_error(1, "ds_fan: too many channels");
-  cudaFuncSetAttribute(ds_fan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(ds_fan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((T + FAN_TF - 1) / FAN_TF, (KP + FAN_KC - 1) / FAN_KC, B);
-  ds_fan_kernel<<<grid, 256, smem, st>>>(spec, T, M, N, steer_fx, D, out);
+  ds_fan_kernel<false><<<grid, 256, smem, st>>>(spec, T, M, N, steer_fx, nullptr, D, out);
+  MCAG_CHECK_LAUNCH();
+  return 0;
+}
+
+// filter-and-sum fan: weights [D][M][KP] float2 (pad bins ignored)
+int k_fs_fan(const float2 *spec, int B, int T, int M, int N, const float2 *weights, int D, float2 *out, cudaStream_t st) {
+  if (B <= 0 || T <= 0) return 0;
+  const int KP = spec_pitch(N);
+  size_t smem = sizeof(float2) * FAN_TF * M * FAN_KC;
+  if (smem > 200 * 1024) return mcag_set_error(1, "fs_fan: too many channels");
+  cudaFuncSetAttribute(ds_fan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid((T + FAN_TF - 1) / FAN_TF, (KP + FAN_KC - 1) / FAN_KC, B);
+  ds_fan_kernel<true><<<grid, 256, smem, st>>>(spec, T, M, N, nullptr, weights, D, out);
   MCAG_CHECK_LAUNCH();
   return 0;
 }

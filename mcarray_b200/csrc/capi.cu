@@ -439,8 +439,14 @@ int mcag_create(const mcag_config *cfg, mcag_proc *out) {
     if (cfg->emit & MCAG_EMIT_CURVES) if ((rc = p->curves.alloc(sizeof(float) * B * T * P * p->L))) return fail(rc);
   }
   if (kind == MCAG_KIND_DSFAN) {
-    if (D < 1 || !cfg->steer_turns) return fail(mcag_set_error(MCAG_ERR_INVALID, "steer_turns [D][M] required"));
-    if ((rc = upload_fx(p->steer_fx, cfg->steer_turns, D * M, st))) return fail(rc);
+    if (D < 1 || (!cfg->steer_turns && !cfg->fs_weights)) return fail(mcag_set_error(MCAG_ERR_INVALID, "steer_turns [D][M] or fs_weights [D][M][K] required"));
+    if (cfg->fs_weights) {   // filter-and-sum: loaded per-bin weights, [D][M][KP] float2 on the device
+      std::vector<float2> w(D * M * KP, make_float2(0.f, 0.f));
+      for (size_t dm = 0; dm < D * M; ++dm)
+        for (int k = 0; k < p->K; ++k) w[dm * KP + k] = make_float2((float)cfg->fs_weights[2 * (dm * p->K + k)], (float)cfg->fs_weights[2 * (dm * p->K + k) + 1]);
+      if ((rc = upload(p->steer_tab, w.data(), w.size() * sizeof(float2), st))) return fail(rc);
+      CUF(cudaStreamSynchronize(st));
+    } else if ((rc = upload_fx(p->steer_fx, cfg->steer_turns, D * M, st))) return fail(rc);
     if ((rc = p->beams.alloc(sizeof(float2) * B * T * D * KP))) return fail(rc);
   }
   if (kind == MCAG_KIND_SRP) {
@@ -797,7 +803,9 @@ static int run_frames(mcag_proc p, const float *x_all, long long pitch, int T, i
     PROF(MCAG_PROF_DS_FAN);
     // 16 / 32 / 48 / 64 microphones: the contraction runs on the tensor cores with four consecutive bins of a tile resident in TMEM
     // (fan_tc.cu); other counts take the CUDA-core register-tile kernel.  MCAG_FAN_CUDA_CORES=1 forces the latter (tests compare the two).
-    if (k_ds_fan_tensor_supported(M) && !getenv("MCAG_FAN_CUDA_CORES"))
+    if (p->cfg.fs_weights)
+      OK(k_fs_fan(spec, B, T, M, N, p->steer_tab.as<float2>(), D, p->beams.as<float2>() + o * T * D * KP, st));
+    else if (k_ds_fan_tensor_supported(M) && !getenv("MCAG_FAN_CUDA_CORES"))
       OK(k_ds_fan_tensor(spec, B, T, M, N, p->steer_fx.as<uint64_t>(), D, p->beams.as<float2>() + o * T * D * KP, st));
     else
       OK(k_ds_fan(spec, B, T, M, N, p->steer_fx.as<uint64_t>(), D, p->beams.as<float2>() + o * T * D * KP, st));
@@ -1176,6 +1184,9 @@ int mcag_k_argmax_pack(const float *d_map, long long rows, int D, int d_offset, 
 }
 int mcag_k_ds_fan(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_steer_fx, int D, void *d_out, void *stream) {
   return k_ds_fan((const float2 *)d_spec, B, T, M, N, d_steer_fx, D, (float2 *)d_out, (cudaStream_t)stream);
+}
+int mcag_k_fs_fan(const void *d_spec, int B, int T, int M, int N, const void *d_weights, int D, void *d_out, void *stream) {
+  return k_fs_fan((const float2 *)d_spec, B, T, M, N, (const float2 *)d_weights, D, (float2 *)d_out, (cudaStream_t)stream);
 }
 int mcag_k_srp_channel(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_mic_fx, int D, float *d_srp, void *stream) {
   return k_srp_channel((const float2 *)d_spec, B, T, M, N, d_mic_fx, D, d_srp, (cudaStream_t)stream);

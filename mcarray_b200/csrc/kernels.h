@@ -37,6 +37,7 @@ int k_steer_table(const uint64_t *fx, int DM, int N, float2 *tab, cudaStream_t s
 int k_ds_select(const float2 *spec, int B, int T, int M, int N, const float2 *steer_tab, const int32_t *cells, int S, int C_out, float2 *out,
                 cudaStream_t st);
 int k_ds_fan(const float2 *spec, int B, int T, int M, int N, const uint64_t *steer_fx, int D, float2 *out, cudaStream_t st);
+int k_fs_fan(const float2 *spec, int B, int T, int M, int N, const float2 *weights /* [D][M][KP] */, int D, float2 *out, cudaStream_t st);
 
 // srp.cu
 int k_srp_channel(const float2 *spec, int B, int T, int M, int N, const uint64_t *mic_fx, int D, float *srp, cudaStream_t st);

@@ -360,6 +360,22 @@ class DelayAndSumFan(Processor):
         return self.fetch(capi.OUT_BEAMS, (B, T, self.info.n_dirs, self.info.spectrum_pitch))[..., : self.info.one_sided_length]
 
 
+class FilterAndSumFan(Processor):
+    """Filter-and-sum beamformer (BASELINE.json north_star; no reference class): D beams with loaded per-bin complex weights
+    W [D][M][N/2+1], Y[d][k] = 1/M sum_c X_c[k] W[d][c][k].  With W = exp(j k phi_c(d)) it is DelayAndSumFan."""
+
+    def __init__(self, sampleRate, n_channels, frame_size, weights, n_streams=1, max_frames_per_call=64):
+        w = np.ascontiguousarray(weights, dtype=np.complex128)
+        D, M, K = w.shape
+        assert M == n_channels and K == frame_size // 2 + 1
+        super().__init__(kind=capi.KIND_DSFAN, sample_rate=sampleRate, frame_size=frame_size, hop=frame_size // 2, n_channels=M, n_streams=n_streams,
+                         max_frames_per_call=max_frames_per_call, n_dirs=D, fs_weights=w.view(np.float64).reshape(-1))
+
+    def beams(self):
+        B, T = self._bt()
+        return self.fetch(capi.OUT_BEAMS, (B, T, self.info.n_dirs, self.info.spectrum_pitch))[..., : self.info.one_sided_length]
+
+
 class SrpPhat(Processor):
     """BASELINE config 4: SRP-PHAT energy map over a direction grid (channel form), smoothing + selectDOA as SteeringBeamforming."""
 

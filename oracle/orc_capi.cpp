@@ -390,6 +390,26 @@ extern "C" void orc_ds_fan(const double *spec, int T, int M, int N, int fs, cons
     for (int d = 0; d < D; ++d) ds_beamform(spec + size_t(t) * M * ccs, M, ccs, fs, mic_x, doas[d], out + (size_t(t) * D + d) * ccs);
 }
 
+// Filter-and-sum fan (BASELINE.json north_star; no reference class): Beamformer::processFrame (Beamformer.cpp:56-70) with the generated
+// phasor exp(j k phi_c) replaced by a loaded complex weight W[d][c][k]: channels added in index order, then divided by M.
+// spec [T][M][ccs], W [D][M][K] complex (re, im), out [T][D][ccs].
+extern "C" void orc_fs_fan(const double *spec, int T, int M, int N, const double *W, int D, double *out) {
+  const int ccs = N + 2, K = N / 2 + 1;
+  for (int t = 0; t < T; ++t)
+    for (int d = 0; d < D; ++d) {
+      double *o = out + (size_t(t) * D + d) * ccs;
+      std::fill(o, o + ccs, 0.0);
+      for (int c = 0; c < M; ++c) {
+        const double *x = spec + (size_t(t) * M + c) * ccs, *w = W + (size_t(d) * M + c) * 2 * K;
+        for (int k = 0; k < K; ++k) {
+          o[2 * k] += x[2 * k] * w[2 * k] - x[2 * k + 1] * w[2 * k + 1];
+          o[2 * k + 1] += x[2 * k] * w[2 * k + 1] + x[2 * k + 1] * w[2 * k];
+        }
+      }
+      for (int i = 0; i < ccs; ++i) o[i] /= M;
+    }
+}
+
 // Generalised far-field geometry: per-mic advance tau_m(d) = (p_m . u_d)/c*fs, pair delay
 // tau_ij(d) = tau_j(d) - tau_i(d).  On an ascending x-axis array with u = (sin th, cos th, 0) this is the
 // reference's dist*sin(th)/c*fs up to its float rounding.

@@ -294,6 +294,15 @@ def ds_fan(spec, N, fs, mic_x, doas):
     return out.view(np.complex128)
 
 
+def fs_fan(spec, N, W):
+    """filter-and-sum fan: spec [T][M][K] complex, W [D][M][K] complex -> [T][D][K] complex"""
+    s = _ccs(spec); T, M = s.shape[0], s.shape[1]
+    W = np.ascontiguousarray(W, dtype=np.complex128); D = W.shape[0]
+    out = np.zeros((T, D, N + 2))
+    lib().orc_fs_fan(_dp(s), C.c_int(T), C.c_int(M), C.c_int(N), _dp(W.view(np.float64)), C.c_int(D), _dp(out))
+    return out.view(np.complex128)
+
+
 def mic_tau(xyz, fs, dirs):
     xyz = np.ascontiguousarray(xyz, dtype=np.float64); dirs = np.ascontiguousarray(dirs, dtype=np.float64)
     out = np.zeros((len(xyz), len(dirs)))

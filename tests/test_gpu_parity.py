@@ -476,6 +476,28 @@ def test_ds_fan_config3_parity(mb, orc):
     assert abs(int(np.argmax(pw)) - (25 + 90)) <= 1     # the fan peaks at the source azimuth
 
 
+def test_filter_and_sum_fan_parity(mb, orc):
+    """filter-and-sum (loaded per-bin complex weights) against the oracle on random weights, and with delay phasors as weights against
+    the delay-and-sum fan of the same processor family"""
+    fs, N, M, D = 16000, 512, 6, 9
+    xs = (np.arange(M) - 2.5) * 0.05
+    xyz = scenes.linear_array(xs)
+    x = scenes.far_field_scene(xyz, fs, 6 * (N // 2) + N, scenes.azimuth_dirs([0.4]), seed=9).astype(np.float32)
+    S = orc.stft(x.astype(np.float64), N, N // 2)
+    rng = np.random.default_rng(3)
+    W = rng.standard_normal((D, M, N // 2 + 1)) + 1j * rng.standard_normal((D, M, N // 2 + 1))
+    p = mb.FilterAndSumFan(fs, M, N, W, max_frames_per_call=16)
+    p.process(x)
+    assert_close(p.beams()[0], orc.fs_fan(S, N, W.astype(np.complex64)), (2,), "filter-and-sum beams")
+    doas = np.deg2rad(np.arange(-80, 81, 20.0))
+    k = np.arange(N // 2 + 1)
+    phi = 2 * np.pi * fs / N / 346.1 * xs[None, :] * np.cos(doas[:, None] + np.pi / 2)
+    q = mb.FilterAndSumFan(fs, M, N, np.exp(1j * phi[:, :, None] * k[None, None, :]), max_frames_per_call=16)
+    r = mb.DelayAndSumFan(fs, xyz, N, doas, max_frames_per_call=16)
+    q.process(x); r.process(x)
+    assert_close(q.beams()[0], r.beams()[0], (2,), "filter-and-sum with delay phasors vs delay-and-sum")
+
+
 def test_srp_config4_parity(mb, orc):
     """BASELINE config 4 (reduced): 64-mic 8x8 planar array, 3600-direction az x el grid, N = 1024; energy map and argmax."""
     fs, N = 48000, 1024

@@ -118,6 +118,21 @@ def test_generalisation_reduces_to_reference(orc):
     assert np.max(np.abs(ref_tau - gen)) < 2e-5  # float rounding of a <= 30-sample delay
 
 
+def test_filter_and_sum_reduces_to_delay_and_sum(orc):
+    """the filter-and-sum restatement with W[d][c][k] = exp(j k phi_c(d)) (Beamformer.cpp:59) is the delay-and-sum fan"""
+    fs, N, M = 16000, 512, 6
+    xs = (np.arange(M) - 2.5) * 0.05
+    xyz = scenes.linear_array(xs)
+    x = scenes.far_field_scene(xyz, fs, 3 * N, scenes.azimuth_dirs([0.4]), seed=9)
+    S = orc.stft(x, N, N // 2)
+    doas = np.deg2rad(np.arange(-90, 91, 30.0))
+    k = np.arange(N // 2 + 1)
+    phi = 2 * np.pi * fs / N / 346.1 * xs[None, :] * np.cos(doas[:, None] + np.pi / 2)      # [D][M]
+    W = np.exp(1j * phi[:, :, None] * k[None, None, :])
+    a, b = orc.fs_fan(S, N, W), orc.ds_fan(S, N, fs, xs, doas)
+    assert np.max(np.abs(a - b)) <= 1e-9 * np.max(np.abs(b))
+
+
 def test_channel_form_equals_pair_form(orc):
     """sum_{i<j} Re(G_ij e^{jw tau_ij}) == 1/2(|sum_m U_m e^{-jw tau_m}|^2 - M)."""
     fs, N = 48000, 512
