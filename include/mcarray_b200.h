@@ -212,6 +212,8 @@ int mcag_k_phase_fx(const double *h_turns, long long n, uint64_t *d_fx, void *st
 int mcag_k_stft_tdoa(const float *d_x, long long row_pitch, int B, int T, int M, int N, int hop, int max_lag, const float *d_win, const void *d_tw,
                      void *d_spec, float *d_chan_pow, float *d_curves, int32_t *d_lags, void *stream);
 int mcag_k_gcc_tau(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_pair_fx, int D, float *d_corr, void *stream);
+/* the same on the tensor cores (tcgen05, 3xTF32): per pair a GEMM over the bins, D <= 64 delays; what the processors run for such grids */
+int mcag_k_gcc_tau_tensor(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_pair_fx, int D, float *d_corr, void *stream);
 int mcag_k_pair_sum(const float *d_corr, long long BT, int P, int D, float scale, float *d_esum, void *stream);
 int mcag_k_energy_scan(const float *d_esum, int B, int T, int D, float a, const unsigned char *d_active, float *d_state, float *d_energy, void *stream);
 int mcag_k_select_doa(const float *d_energy, long long BT, int D, int n_pairs, int S, int32_t *d_idx, float *d_prob, void *stream);

@@ -188,6 +188,7 @@ struct mcag_proc_s {
   DevBuf fifo[2]; int fifo_cur = 0; long long fifo_cap = 0; int fill = 0;
   DevBuf stage_in, stage_out;   // device staging for non-f32 input / output conversion
   DevBuf win, tw, spec, chan_pow, chan_raw, power_db, active, gate;
+  DevBuf tau_tab;   // delay operand of the tcgen05 tau-grid GCC (gcc_tc.cu), built once from pair_fx
   DevBuf pair_fx, corr, esum, energy, energy_state, raw_idx, raw_prob, cells, prob, cell_state, prob_state;
   DevBuf steer_fx, steer_tab, beams, tail[2], out_dev; int tail_cur = 0;
   DevBuf lags, curves, curve_state, fg, est, track_doa, track_prob;
@@ -377,8 +378,16 @@ int mcag_create(const mcag_config *cfg, mcag_proc *out) {
         if ((rc = p->srp_ws.alloc(k_srp_tensor_workspace_bytes((long long)B * T, p->M, N, p->D)))) return fail(rc);
       }
     }
-    if (p->srp_form != 2)
+    if (p->srp_form != 2) {
       if ((rc = p->corr.alloc(sizeof(float) * B * T * P * D))) return fail(rc);
+      // pair form on the tensor cores (gcc_tc.cu: a GEMM over the bins per pair) for grids of at most 64 delays; MCAG_GCC_CUDA_CORES=1
+      // keeps the CUDA-core register-tile kernel (tests compare the two)
+      if (k_gcc_tau_tc_supported((int)D) && !getenv("MCAG_GCC_CUDA_CORES")) {
+        if ((rc = p->tau_tab.alloc(k_gcc_tau_tc_table_bytes((int)P, N)))) return fail(rc);
+        if ((rc = k_gcc_tau_tc_build(p->pair_fx.as<uint64_t>(), (int)P, (int)D, N, p->tau_tab.as<float>(), st))) return fail(rc);
+        CUF(cudaStreamSynchronize(st));
+      }
+    }
   }
   if (loc || kind == MCAG_KIND_SRP) {
     if ((rc = p->esum.alloc(sizeof(float) * B * T * D))) return fail(rc);
@@ -522,7 +531,7 @@ void mcag_destroy(mcag_proc p) {
   if (p->copy_in) cudaStreamSynchronize(p->copy_in);
   if (p->copy_out) cudaStreamSynchronize(p->copy_out);
   DevBuf *all[] = {&p->fifo[0], &p->fifo[1], &p->stage_in, &p->stage_out, &p->win, &p->tw, &p->spec, &p->chan_pow, &p->chan_raw, &p->power_db,
-                   &p->active, &p->gate, &p->pair_fx, &p->corr, &p->esum, &p->energy, &p->energy_state, &p->raw_idx, &p->raw_prob, &p->cells,
+                   &p->active, &p->gate, &p->tau_tab, &p->pair_fx, &p->corr, &p->esum, &p->energy, &p->energy_state, &p->raw_idx, &p->raw_prob, &p->cells,
                    &p->prob, &p->cell_state, &p->prob_state, &p->steer_fx, &p->steer_tab, &p->beams, &p->tail[0], &p->tail[1], &p->out_dev,
                    &p->lags, &p->curves, &p->curve_state, &p->fg, &p->est, &p->track_doa, &p->track_prob, &p->mic_fx, &p->srp_ws, &p->H, &p->H2, &p->thr, &p->stats, &p->gains, &p->Q,
                    &p->noise, &p->dec, &p->qtrace, &p->mask_tab, &p->band_raw, &p->band_energy, &p->floor_pow, &p->band_cells, &p->mb_raw_cell, &p->mb_raw_prob, &p->mb_lohi};
@@ -728,8 +737,8 @@ static int run_frames(mcag_proc p, const float *x_all, long long pitch, int T, i
       float *corr = p->corr.as<float>() + o * T * P * D;
       {
         PROF(MCAG_PROF_GCC_TAU);
-        OK(k_gcc_tau(spec, B, T, M, N, p->pair_fx.as<uint64_t>(), D, corr, st));
-        p->launches += (D <= 40) ? 1 : (D + 63) / 64;
+        if (p->tau_tab.p) { OK(k_gcc_tau_tc(spec, B, T, M, N, p->tau_tab.as<float>(), D, corr, st)); p->launches++; }
+        else { OK(k_gcc_tau(spec, B, T, M, N, p->pair_fx.as<uint64_t>(), D, corr, st)); p->launches += (D <= 40) ? 1 : (D + 63) / 64; }
       }
       PROF(MCAG_PROF_ENERGY);
       OK(k_pair_sum(corr, BT, P, D, b, esum, st));
@@ -750,8 +759,8 @@ static int run_frames(mcag_proc p, const float *x_all, long long pitch, int T, i
     float *corr = p->corr.as<float>() + o * T * D;
     {
       PROF(MCAG_PROF_GCC_TAU);
-      OK(k_gcc_tau(spec, B, T, 2, N, p->pair_fx.as<uint64_t>(), D, corr, st));
-      p->launches += (D <= 40) ? 1 : (D + 63) / 64;
+      if (p->tau_tab.p) { OK(k_gcc_tau_tc(spec, B, T, 2, N, p->tau_tab.as<float>(), D, corr, st)); p->launches++; }
+      else { OK(k_gcc_tau(spec, B, T, 2, N, p->pair_fx.as<uint64_t>(), D, corr, st)); p->launches += (D <= 40) ? 1 : (D + 63) / 64; }
     }
     {
       PROF(MCAG_PROF_CURVE_SCAN);
@@ -1169,6 +1178,17 @@ int mcag_k_stft_tdoa(const float *d_x, long long row_pitch, int B, int T, int M,
 }
 int mcag_k_gcc_tau(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_pair_fx, int D, float *d_corr, void *stream) {
   return k_gcc_tau((const float2 *)d_spec, B, T, M, N, d_pair_fx, D, d_corr, (cudaStream_t)stream);
+}
+int mcag_k_gcc_tau_tensor(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_pair_fx, int D, float *d_corr, void *stream) {
+  if (!k_gcc_tau_tc_supported(D)) return mcag_set_error(MCAG_ERR_INVALID, "gcc_tau_tensor: at most 64 delays");
+  cudaStream_t st = (cudaStream_t)stream;
+  void *tab = nullptr;
+  const int P = M * (M - 1) / 2;
+  CU(cudaMallocAsync(&tab, k_gcc_tau_tc_table_bytes(P, N), st));
+  int rc = k_gcc_tau_tc_build(d_pair_fx, P, D, N, (float *)tab, st);
+  if (!rc) rc = k_gcc_tau_tc((const float2 *)d_spec, B, T, M, N, (const float *)tab, D, d_corr, st);
+  cudaFreeAsync(tab, st);
+  return rc;
 }
 int mcag_k_pair_sum(const float *d_corr, long long BT, int P, int D, float scale, float *d_esum, void *stream) {
   return k_pair_sum(d_corr, BT, P, D, scale, d_esum, (cudaStream_t)stream);

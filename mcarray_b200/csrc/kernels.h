@@ -20,6 +20,12 @@ int k_stft_tdoa(const float *x, long long row_pitch, int B, int T, int M, int N,
                 float2 *spec, float *chan_pow, float *curves, int32_t *lags, cudaStream_t st);
 int k_gcc_tau(const float2 *spec, int B, int T, int M, int N, const uint64_t *pair_fx, int D, float *corr, cudaStream_t st);
 
+// gcc_tc.cu (tcgen05): the tau-grid GCC-PHAT of one pair as a GEMM over the bins (D <= 64 delays)
+bool k_gcc_tau_tc_supported(int D);
+size_t k_gcc_tau_tc_table_bytes(int P, int N);
+int k_gcc_tau_tc_build(const uint64_t *pair_fx, int P, int D, int N, float *table, cudaStream_t st);   // once per processor
+int k_gcc_tau_tc(const float2 *spec, int B, int T, int M, int N, const float *table, int D, float *corr, cudaStream_t st);
+
 // doa.cu
 int k_pair_sum(const float *corr, long long BT, int P, int D, float scale, float *esum, cudaStream_t st);
 int k_energy_scan(const float *esum, int B, int T, int D, float a, const unsigned char *active, float *state, float *energy, cudaStream_t st);

@@ -576,6 +576,35 @@ def test_srp_tensor_kernel_vs_cuda_core_kernel(mb, M, BT, D, N):
     assert np.max(np.abs(a - b) / (ATOL + RTOL * scale)) <= 1.0, np.max(np.abs(a - b) / scale)
 
 
+@pytest.mark.parametrize("M,BT,D,N", [(2, 300, 61, 512), (4, 130, 37, 2048), (3, 5, 64, 256), (6, 129, 1, 1024)])
+def test_gcc_tau_tensor_kernel_vs_cuda_core_kernel(mb, M, BT, D, N):
+    """tau-grid GCC-PHAT of every pair as a tcgen05 GEMM over the bins (gcc_tau_tc_kernel) against the CUDA-core register-tile kernel on
+    the same random spectra: partial frame tiles, every frame size, silent bins, 1..64 delays"""
+    import ctypes as C
+    import torch
+    from mcarray_b200 import capi
+    lib = capi.lib()
+    g = torch.Generator(device="cuda").manual_seed(M * 1000 + BT)
+    KP, P = N // 2 + 2, M * (M - 1) // 2
+    spec = torch.randn(BT, M, KP, 2, device="cuda", generator=g) * 100
+    spec[:, :, N // 2 + 1:] = 0
+    spec[:, :, 0, 1] = 0; spec[:, :, N // 2, 1] = 0
+    spec[3 % BT, 1, 7] = 0                                   # a silent bin: PHAT of 0 is 0
+    rng = np.random.default_rng(D)
+    turns = np.ascontiguousarray(rng.uniform(-30, 30, size=(P, D)) / N)
+    fx = torch.empty(P * D, dtype=torch.int64, device="cuda")
+    capi.check(lib.mcag_k_phase_fx(capi.dp(turns), C.c_longlong(P * D), capi.vp(fx), None))
+    out_c = torch.zeros(BT, P, D, device="cuda"); out_t = torch.zeros(BT, P, D, device="cuda")
+    torch.cuda.synchronize()
+    capi.check(lib.mcag_k_gcc_tau(capi.vp(spec), 1, BT, M, N, capi.vp(fx), D, capi.vp(out_c), None))
+    capi.check(lib.mcag_k_gcc_tau_tensor(capi.vp(spec), 1, BT, M, N, capi.vp(fx), D, capi.vp(out_t), None))
+    torch.cuda.synchronize()
+    a, b = out_t.cpu().numpy(), out_c.cpu().numpy()
+    assert np.isfinite(a).all()
+    scale = np.max(np.abs(b), axis=(1, 2), keepdims=True)      # the frame's largest correlation (a single delay can sit at zero)
+    assert np.max(np.abs(a - b) / (ATOL + RTOL * scale)) <= 1.0, np.max(np.abs(a - b) / scale)
+
+
 @pytest.mark.parametrize("M,BT,D,N", [(32, 200, 181, 512), (16, 130, 70, 256), (64, 5, 300, 1024), (48, 128, 128, 2048)])
 def test_ds_fan_tensor_kernel_vs_cuda_core_kernel(mb, M, BT, D, N):
     """K4 fan on tcgen05 (srp_tc_kernel<NKC, FAN>: 3xTF32 contraction of the raw spectra, beams written per bin) against the CUDA-core
