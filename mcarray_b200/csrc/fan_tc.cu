@@ -62,8 +62,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ds_fan_tc_kernel(const FtParams
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < FT_STAGES; ++s) { mbar_init(&full_a[s], FT_A_THREADS); mbar_init(&full_b[s], FT_B_THREADS); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1); mbar_init(tmem_empty, FT_EPI_THREADS);
+    for (int s = 0; s < FT_STAGES; ++s) { mbar_init(&full_a[s], FT_A_THREADS / 32); mbar_init(&full_b[s], FT_B_THREADS / 32); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1); mbar_init(tmem_empty, FT_EPI_THREADS / 32);
   }
   if (warp == 0) {   // all 512 TMEM columns: four bins x (64 Re + 64 Im) columns; 1 CTA per SM
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ds_fan_tc_kernel(const FtParams
             *reinterpret_cast<float4 *>(st + FT_A_BYTES + a_row + off) = make_float4(x[4 * q] - h0, x[4 * q + 1] - h1, x[4 * q + 2] - h2, x[4 * q + 3] - h3);
           }
           fence_async_smem();
-          mbar_arrive(&full_a[stage]);
+          mbar_arrive_warp(&full_a[stage]);
           if (++stage == FT_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ds_fan_tc_kernel(const FtParams
             *reinterpret_cast<float4 *>(bl + b_im + q_im) = make_float4(sl0, cl0, sl1, cl1);
           }
           fence_async_smem();
-          mbar_arrive(&full_b[stage]);
+          mbar_arrive_warp(&full_b[stage]);
           if (++stage == FT_STAGES) { stage = 0; phase ^= 1; }
         }
     }
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ds_fan_tc_kernel(const FtParams
         }
       }
       tc_fence_before();
-      mbar_arrive(tmem_empty);
+      mbar_arrive_warp(tmem_empty);
       acc_phase ^= 1;
     }
   }

@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(GT2_THREADS, 1) gcc_tau_tc_kernel(const Gt2Par
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < GT2_STAGES; ++s) { mbar_init(&full_a[s], GT2_PROD_THREADS); mbar_init(&full_b[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], GT2_EPI_THREADS); }
+    for (int s = 0; s < GT2_STAGES; ++s) { mbar_init(&full_a[s], GT2_PROD_THREADS / 32); mbar_init(&full_b[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], GT2_EPI_THREADS / 32); }
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_slot)) : "memory");
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(GT2_THREADS, 1) gcc_tau_tc_kernel(const Gt2Par
           *reinterpret_cast<float4 *>(st + GT2_A_BYTES + off) = make_float4(g0.x - h0, g0.y - h1, g1.x - h2, g1.y - h3);
         }
         fence_async_smem();
-        mbar_arrive(&full_a[stage]);
+        mbar_arrive_warp(&full_a[stage]);
         if (++stage == GT2_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(GT2_THREADS, 1) gcc_tau_tc_kernel(const Gt2Par
         }
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
+      mbar_arrive_warp(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }

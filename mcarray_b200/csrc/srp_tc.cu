@@ -123,8 +123,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) srp_tc_kernel(const __grid_cons
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_a[s], 1); mbar_init(&full_b[s], TC_GEN_THREADS); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], TC_EPI_THREADS); }
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_a[s], 1); mbar_init(&full_b[s], TC_GEN_THREADS / 32); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], TC_EPI_THREADS / 32); }
   }
   if (warp == 1) {   // TMEM: all 512 columns (two 256-column accumulators); 1 CTA per SM
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) srp_tc_kernel(const __grid_cons
             *reinterpret_cast<float4 *>(bl + row_im + q) = make_float4(sl0, cl0, sl1, cl1);
           }
           fence_async_smem();            // generic-proxy stores -> visible to the tensor core (async proxy)
-          mbar_arrive(&full_b[stage]);
+          mbar_arrive_warp(&full_b[stage]);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
     }
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) srp_tc_kernel(const __grid_cons
           for (int i = 0; i < 16; ++i) sum[j * 16 + i] = fmaf(vi[i], vi[i], fmaf(vr[i], vr[i], sum[j * 16 + i]));
         }
         tc_fence_before();
-        mbar_arrive(&tmem_empty[acc]);
+        mbar_arrive_warp(&tmem_empty[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       if (t < p.BT) {
@@ -337,8 +337,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) srp_tc_small_kernel(const TsPar
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < TS_STAGES; ++s) { mbar_init(&full[s], TS_PROD_THREADS); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], TS_EPI_THREADS); }
+    for (int s = 0; s < TS_STAGES; ++s) { mbar_init(&full[s], TS_PROD_THREADS / 32); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], TS_EPI_THREADS / 32); }
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) srp_tc_small_kernel(const TsPar
               *reinterpret_cast<float4 *>(bl + b_im + off) = make_float4(sl0, cl0, sl1, cl1);
             }
             fence_async_smem();
-            mbar_arrive(&full[stage]);
+            mbar_arrive_warp(&full[stage]);
             if (++stage == TS_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) srp_tc_small_kernel(const TsPar
           for (int i = 0; i < 8; ++i) sum[j * 8 + i] = fmaf(vi[i], vi[i], fmaf(vr[i], vr[i], sum[j * 8 + i]));
         }
         tc_fence_before();
-        mbar_arrive(&tmem_empty[acc]);
+        mbar_arrive_warp(&tmem_empty[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       if (t < p.BT) {

@@ -10,6 +10,13 @@ namespace mcag {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// one arrival per warp: every lane has made its writes (and its proxy fence / tcgen05 fence) before __syncwarp, lane 0's release-arrive then
+// covers them.  512 per-thread arrivals on one barrier word serialise in the shared-memory atomic unit; 16 do not.  Barriers signalled this
+// way are initialised with the WARP count.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t *bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 // bounded spin: a pipeline bug traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
   uint32_t done = 0;
