@@ -2,7 +2,9 @@
 // framing + overlap-add of ShortTimeProcess::process that every reference processor runs
 // (SourceSeparationAndLocalisation.cpp:51-52, SourceLocalisation.cpp:51-52, BinauralLocalisation.cpp:320-322,
 // FastBinauralMasking.cpp:57; consumer mcabeamf.cpp:112-119).
+#include <cstdlib>
 #include "fft.cuh"
+#include "fft16.cuh"
 #include "kernels.h"
 
 namespace mcag {
@@ -129,6 +131,102 @@ __global__ void __launch_bounds__(G *(N / 16)) stft_kernel(const float *__restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// K1 for N = 512 on the register-resident engine of fft16.cuh: the same persistent work items and bulk-copy staging as stft_kernel, one
+// HALF-WARP per frame (HW frames of a row per item).  Per frame the shared memory sees the staged samples once, the window (one wavefront
+// per warp: both half-warps read the same entries), the inter-pass twiddles (likewise) and one 2 KB transpose: 64 wavefronts against 197.
+// ---------------------------------------------------------------------------------------------------
+#ifndef MCAG_STFT512_HW
+#define MCAG_STFT512_HW 8
+#endif
+#ifndef MCAG_STFT512_MINB
+#define MCAG_STFT512_MINB 6
+#endif
+template <int HW>
+__global__ void __launch_bounds__(HW * 16, MCAG_STFT512_MINB) stft512_hw_kernel(const float *__restrict__ x, long long row_pitch, int M, int T, int hop,
+                                                              const float *__restrict__ win, const float2 *__restrict__ tw_g,
+                                                              float2 *__restrict__ spec, float *__restrict__ chan_pow, float *__restrict__ chan_raw,
+                                                              int tiles_per_row, long long n_items, int xlen) {
+  constexpr int N = 512, KP = spec_pitch(N), F = HW, NT = HW * 16;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *s_xb = reinterpret_cast<float2 *>(smem_raw);          // HW transpose buffers
+  float2 *s_t1 = s_xb + HW * kFft16BufLen;
+  float2 *s_w = s_t1 + kFft16TabLen;                            // 256 window pairs
+  float *s_xs = reinterpret_cast<float *>(s_w + N / 2);         // 2 x xlen staged samples
+  __shared__ __align__(8) uint64_t s_bar[2];
+
+  const int tid = threadIdx.x, l16 = tid & 15, f = tid >> 4;
+  const bool bulk = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((row_pitch & 3) == 0) && ((hop & 3) == 0);
+  if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
+  fft16_load_table(s_t1, tw_g, tid, NT);
+  for (int i = tid; i < N / 2; i += NT) s_w[i] = make_float2(win[2 * i], win[2 * i + 1]);
+  const float2 wl = tw_g[l16];
+  __syncthreads();
+
+  auto item_src = [&](long long item, int &row, int &t0, int &nf) {   // n_items < 2^31 (checked by the launcher): 32-bit division
+    row = (int)((unsigned)item / (unsigned)tiles_per_row);
+    t0 = ((int)item - row * tiles_per_row) * F;
+    nf = min(F, T - t0);
+    return x + (long long)row * row_pitch + (long long)t0 * hop;
+  };
+  auto issue = [&](long long item, int slot) {   // thread 0 only
+    int row, t0, nf;
+    const float *src = item_src(item, row, t0, nf);
+    const uint32_t bytes = (uint32_t)((nf - 1) * hop + N) * 4u;
+    mbar_expect_tx(&s_bar[slot], bytes);
+    bulk_g2s(s_xs + slot * xlen, src, bytes, &s_bar[slot]);
+  };
+
+  float2 *xbuf = s_xb + f * kFft16BufLen;
+  if (bulk && tid == 0 && (long long)blockIdx.x < n_items) issue(blockIdx.x, 0);
+  int it = 0;
+  for (long long item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    const int slot = it & 1;
+    int row, t0, nf;
+    const float *src = item_src(item, row, t0, nf);
+    float *s_x = s_xs + slot * xlen;
+    if (bulk) {
+      if (tid == 0 && item + gridDim.x < n_items) issue(item + gridDim.x, slot ^ 1);
+      mbar_wait(&s_bar[slot], (uint32_t)(it >> 1) & 1u);
+    } else {
+      const int nsamp = (nf - 1) * hop + N;
+      for (int i = tid; i < nsamp; i += NT) s_x[i] = src[i];
+      __syncthreads();
+    }
+    const int b = (int)((unsigned)row / (unsigned)M), m = row - b * M;
+    // a half-warp past the end of the row repeats the last frame (its partner half-warp needs it for the warp-wide shuffles) and stores nothing
+    const bool live = f < nf;
+    const int fr = live ? f : nf - 1;
+    const float2 *xs = reinterpret_cast<const float2 *>(s_x + fr * hop);   // hop is even -> 8-byte aligned
+    float2 v[16];
+#pragma unroll
+    for (int a = 0; a < 16; ++a) {
+      const float2 s = xs[16 * a + l16], w = s_w[16 * a + l16];
+      v[a] = make_float2(s.x * w.x, s.y * w.y);
+    }
+    fft256_hw<false>(v, xbuf, s_t1, l16);
+    const long long orow = ((long long)b * T + (t0 + f)) * M + m;
+    float2 *out = spec + orow * KP;
+    float nyq, pw = 0.f, x0 = 0.f;
+    fft16_real_post(v, wl, l16, nyq, [&](int d, float2 X) {
+      if (live) out[l16 + 16 * d] = X;
+      if (d == 0) x0 = X.x;
+      pw += X.x * X.x + X.y * X.y;
+    });
+    // Parseval weights: 1 for k = 0 and the Nyquist bin, 2 for the others; the plain sum over the K bins beside it
+    float pr = pw + (l16 == 0 ? nyq * nyq : 0.f);
+    pw = 2.f * pw - (l16 == 0 ? x0 * x0 - nyq * nyq : 0.f);
+    if (chan_pow) pw = hw_sum(pw);
+    if (chan_raw) pr = hw_sum(pr);
+    if (live && l16 == 0) {
+      *reinterpret_cast<float4 *>(out + N / 2) = make_float4(nyq, 0.f, 0.f, 0.f);   // the Nyquist bin and the pad bin
+      if (chan_pow) chan_pow[orow] = pw / ((float)N * (float)N);
+      if (chan_raw) chan_raw[orow] = pr;
+    }
+    __syncthreads();   // all frames of the item are done with s_x[slot] before a later copy lands in it
+  }
+}
+
 // power for the small-TPF case is handled by a dedicated reduction kernel (frame_power_kernel below), which is
 // also the generic path: spec [rows] -> pow[rows], rows = B*T*M.
 __global__ void frame_power_kernel(const float2 *__restrict__ spec, long long rows, int N, float *__restrict__ pow) {
@@ -234,6 +332,34 @@ __global__ void __launch_bounds__(G *(N / 16)) istft_kernel(const float2 *__rest
   }
 }
 
+static int device_sm_count() {
+  static int sm_count = 0, dev_cached = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != dev_cached) { cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); dev_cached = dev; }
+  return sm_count;
+}
+
+// N = 512 on the half-warp engine (MCAG_STFT_STOCKHAM=1 keeps the shared-memory engine for A/B runs)
+static int launch_stft512_hw(const float *x, long long row_pitch, int rows, int M, int T, int hop, const float *win, const float2 *tw, float2 *spec,
+                             float *chan_pow, float *chan_raw, cudaStream_t st) {
+  constexpr int HW = MCAG_STFT512_HW, N = 512;
+  const int xlen = (HW - 1) * hop + N;   // hop is even; the bulk path needs hop % 4 == 0, which keeps both slots 16-byte aligned
+  const size_t smem = sizeof(float2) * (HW * kFft16BufLen + kFft16TabLen + N / 2) + sizeof(float) * 2 * (size_t)xlen;
+  auto kern = stft512_hw_kernel<HW>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, HW * 16, smem);
+  if (per_sm < 1) per_sm = 1;
+  const int tiles_per_row = (T + HW - 1) / HW;
+  const long long n_items = (long long)tiles_per_row * rows, cap = (long long)device_sm_count() * per_sm;
+  if (n_items >= (1ll << 31)) return mcag_set_error(1, "stft: too many frames in one call");
+  kern<<<(unsigned)(n_items < cap ? n_items : cap), HW * 16, smem, st>>>(x, row_pitch, M, T, hop, win, tw, spec, chan_pow, chan_pow ? chan_raw : nullptr,
+                                                                         tiles_per_row, n_items, xlen);
+  MCAG_CHECK_LAUNCH();
+  return 0;
+}
+
 template <int N> static int launch_stft(const float *x, long long row_pitch, int rows, int M, int T, int hop, const float *win,
                                         const float2 *tw, float2 *spec, float *chan_pow, float *chan_raw, cudaStream_t st) {
   constexpr int NC = N / 2, TPF = NC / 8;
@@ -293,7 +419,11 @@ int k_stft(const float *x, long long row_pitch, int rows, int M, int T, int N, i
   if (hop <= 0 || hop > N || (hop & 1) || (N % hop)) return mcag_set_error(1, "stft: hop must be even and divide N");
   switch (N) {
     case 256: return launch_stft<256>(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, chan_raw, st);
-    case 512: return launch_stft<512>(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, chan_raw, st);
+    case 512: {
+      static const bool stockham = getenv("MCAG_STFT_STOCKHAM") != nullptr;
+      if (!stockham) return launch_stft512_hw(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, chan_raw, st);
+      return launch_stft<512>(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, chan_raw, st);
+    }
     case 1024: return launch_stft<1024>(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, chan_raw, st);
     case 2048: return launch_stft<2048>(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, chan_raw, st);
   }

@@ -438,7 +438,8 @@ def test_mask_decisions_vs_oracle(mb, orc):
 @pytest.mark.parametrize("N,method,alg", [(512, "NOISY", "BOTH"), (1024, "FACTOR", "TEMPORAL"), (2048, "FULL", "SPATIAL"), (512, "RELATIVE", "BOTH")])
 def test_mask_fused_kernel_equals_staged_kernels(mb, N, method, alg):
     """mask_fused_kernel (analysis + mask + synthesis in one kernel) against the stft / stats / scan / apply / istft chain on several
-    streams fed in ragged chunks: same decisions and Q trace bit for bit, audio within tolerance, frame powers equal."""
+    streams fed in ragged chunks: same decisions, Q trace and frame powers bit for bit where both run the same FFT schedule (within
+    rounding at N = 512, where they do not), audio within tolerance."""
     fs, d, B = 16000, 0.086, 5
     xyz = scenes.linear_array([0, d])
     x = np.concatenate([scenes.far_field_scene(xyz, fs, 9 * N + 77, scenes.azimuth_dirs([0.0, np.deg2rad(20 + 15 * b)]), seed=300 + b) for b in range(B)]).astype(np.float32)
@@ -451,8 +452,12 @@ def test_mask_fused_kernel_equals_staged_kernels(mb, N, method, alg):
         assert a.shape == b_.shape and f.frames_done == s.frames_done
         if f.frames_done:
             assert np.array_equal(f.decisions(), s.decisions())
-            assert np.array_equal(f.Q(), s.Q())
-            assert np.array_equal(f.power_db(), s.power_db())
+            if N == 512:   # the staged STFT runs the half-warp engine (fft16.cuh), the fused kernel the Stockham engine: rounding differs
+                np.testing.assert_allclose(f.Q(), s.Q(), rtol=2e-5, atol=0)
+                np.testing.assert_allclose(f.power_db(), s.power_db(), rtol=0, atol=1e-4)
+            else:
+                assert np.array_equal(f.Q(), s.Q())
+                assert np.array_equal(f.power_db(), s.power_db())
             hop = f.info.hop
             assert_close(a.T.reshape(-1, hop, 2 * B), b_.T.reshape(-1, hop, 2 * B), (1, 2), f"fused vs staged audio N={N} {method}")
         if pos >= x.shape[1]:
