@@ -206,7 +206,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ds_fan_tc_kernel(const FtParams
     // parts they lack with their neighbour.  What this pattern can reach is measured in tools/ubench/scatter_store2.cu: 16 rows x 32 B
     // per store instruction run at 1.8 TB/s (16 B per lane-row: 1.2 TB/s, 128 B per row: 3.8 TB/s, 512 B: 4.6 TB/s), whoever issues them
     // - a TMA store of the same 32-byte rows was slower still (0.83 ms for the kernel against 0.59 ms).  The stores are therefore 0.3 ms
-    // of this kernel; the next step is 16 bins per row resident in TMEM (N = 32 frames per MMA) behind a shared-memory transpose.
+    // of this kernel.  Sixteen bins per row resident in TMEM (N = 32 frames per MMA, 128-byte rows behind a shared-memory transpose) was
+    // built three ways in round 2 and stayed behind this kernel, see DESIGN.md 4 "what did not work": with a quarter of the frames per
+    // MMA the operand stages quadruple, and the shared-memory write bandwidth of the generated steering operand (32 KB per stage), the
+    // per-instruction issue cost of tcgen05.mma from one elected lane and the 32-byte gathers of the frames operand each became the bound.
     const int e = warp - (1 + (FT_A_THREADS + FT_B_THREADS) / 32);
     const int quarter = warp & 3, fh = e >> 2;   // TMEM lanes 32 quarter..+31 = directions 16 quarter..+15; frames 64 fh..+63 of the tile
     const bool odd = lane & 1;
