@@ -132,9 +132,9 @@ __global__ void __launch_bounds__(G *(N / 16)) stft_kernel(const float *__restri
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K1 for N = 512 on the register-resident engine of fft16.cuh: the same persistent work items and bulk-copy staging as stft_kernel, one
-// HALF-WARP per frame (HW frames of a row per item).  Per frame the shared memory sees the staged samples once, the window (one wavefront
-// per warp: both half-warps read the same entries), the inter-pass twiddles (likewise) and one 2 KB transpose: 64 wavefronts against 197.
+// K1 for N = 512 and N = 1024 on the register-resident engine of fft16.cuh: the same persistent work items and bulk-copy staging as
+// stft_kernel, one HALF-WARP per frame (HW frames of a row per item), N/32 sample pairs per lane.  Per N = 512 frame the shared memory
+// sees the staged samples once, the window, the inter-pass twiddles and one 2 KB transpose: 108 wavefronts (shuffles included) against 197.
 // ---------------------------------------------------------------------------------------------------
 #ifndef MCAG_STFT512_HW
 #define MCAG_STFT512_HW 8
@@ -142,23 +142,29 @@ __global__ void __launch_bounds__(G *(N / 16)) stft_kernel(const float *__restri
 #ifndef MCAG_STFT512_MINB
 #define MCAG_STFT512_MINB 6
 #endif
-template <int HW>
-__global__ void __launch_bounds__(HW * 16, MCAG_STFT512_MINB) stft512_hw_kernel(const float *__restrict__ x, long long row_pitch, int M, int T, int hop,
-                                                              const float *__restrict__ win, const float2 *__restrict__ tw_g,
-                                                              float2 *__restrict__ spec, float *__restrict__ chan_pow, float *__restrict__ chan_raw,
-                                                              int tiles_per_row, long long n_items, int xlen) {
-  constexpr int N = 512, KP = spec_pitch(N), F = HW, NT = HW * 16;
+#ifndef MCAG_STFT1024_HW
+#define MCAG_STFT1024_HW 8
+#endif
+#ifndef MCAG_STFT1024_MINB
+#define MCAG_STFT1024_MINB 1
+#endif
+template <int N, int HW, int MINB>
+__global__ void __launch_bounds__(HW * 16, MINB) stft_hw_kernel(const float *__restrict__ x, long long row_pitch, int M, int T, int hop,
+                                                                 const float *__restrict__ win, const float2 *__restrict__ tw_g,
+                                                                 float2 *__restrict__ spec, float *__restrict__ chan_pow, float *__restrict__ chan_raw,
+                                                                 int tiles_per_row, long long n_items, int xlen) {
+  constexpr int R = N / 32, KP = spec_pitch(N), F = HW, NT = HW * 16;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2 *s_xb = reinterpret_cast<float2 *>(smem_raw);          // HW transpose buffers
-  float2 *s_t1 = s_xb + HW * kFft16BufLen;
-  float2 *s_w = s_t1 + kFft16TabLen;                            // 256 window pairs
+  float2 *s_t1 = s_xb + HW * fft16_buf_len<R>();
+  float2 *s_w = s_t1 + fft16_tab_len<R>();                      // N/2 window pairs
   float *s_xs = reinterpret_cast<float *>(s_w + N / 2);         // 2 x xlen staged samples
   __shared__ __align__(8) uint64_t s_bar[2];
 
   const int tid = threadIdx.x, l16 = tid & 15, f = tid >> 4;
   const bool bulk = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((row_pitch & 3) == 0) && ((hop & 3) == 0);
   if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
-  fft16_load_table(s_t1, tw_g, tid, NT);
+  fft16_load_table<R>(s_t1, tw_g, tid, NT);
   for (int i = tid; i < N / 2; i += NT) s_w[i] = make_float2(win[2 * i], win[2 * i + 1]);
   const float2 wl = tw_g[l16];
   __syncthreads();
@@ -177,7 +183,7 @@ __global__ void __launch_bounds__(HW * 16, MCAG_STFT512_MINB) stft512_hw_kernel(
     bulk_g2s(s_xs + slot * xlen, src, bytes, &s_bar[slot]);
   };
 
-  float2 *xbuf = s_xb + f * kFft16BufLen;
+  float2 *xbuf = s_xb + f * fft16_buf_len<R>();
   if (bulk && tid == 0 && (long long)blockIdx.x < n_items) issue(blockIdx.x, 0);
   int it = 0;
   for (long long item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -198,19 +204,19 @@ __global__ void __launch_bounds__(HW * 16, MCAG_STFT512_MINB) stft512_hw_kernel(
     const bool live = f < nf;
     const int fr = live ? f : nf - 1;
     const float2 *xs = reinterpret_cast<const float2 *>(s_x + fr * hop);   // hop is even -> 8-byte aligned
-    float2 v[16];
+    float2 v[R];
 #pragma unroll
-    for (int a = 0; a < 16; ++a) {
+    for (int a = 0; a < R; ++a) {
       const float2 s = xs[16 * a + l16], w = s_w[16 * a + l16];
       v[a] = make_float2(s.x * w.x, s.y * w.y);
     }
-    fft256_hw<false>(v, xbuf, s_t1, l16);
+    fft_hw<R, false>(v, xbuf, s_t1, l16);
     const long long orow = ((long long)b * T + (t0 + f)) * M + m;
     float2 *out = spec + orow * KP;
     float nyq, pw = 0.f, x0 = 0.f;
-    fft16_real_post(v, wl, l16, nyq, [&](int d, float2 X) {
-      if (live) out[l16 + 16 * d] = X;
-      if (d == 0) x0 = X.x;
+    fft_hw_real_post<R>(v, wl, l16, nyq, [&](int e, float2 X) {
+      if (live) out[l16 + 16 * e] = X;
+      if (e == 0) x0 = X.x;
       pw += X.x * X.x + X.y * X.y;
     });
     // Parseval weights: 1 for k = 0 and the Nyquist bin, 2 for the others; the plain sum over the K bins beside it
@@ -340,13 +346,14 @@ static int device_sm_count() {
   return sm_count;
 }
 
-// N = 512 on the half-warp engine (MCAG_STFT_STOCKHAM=1 keeps the shared-memory engine for A/B runs)
-static int launch_stft512_hw(const float *x, long long row_pitch, int rows, int M, int T, int hop, const float *win, const float2 *tw, float2 *spec,
-                             float *chan_pow, float *chan_raw, cudaStream_t st) {
-  constexpr int HW = MCAG_STFT512_HW, N = 512;
+// N = 512 / 1024 on the half-warp engine (MCAG_STFT_STOCKHAM=1 keeps the shared-memory engine for A/B runs)
+template <int N, int HW, int MINB>
+static int launch_stft_hw(const float *x, long long row_pitch, int rows, int M, int T, int hop, const float *win, const float2 *tw, float2 *spec,
+                          float *chan_pow, float *chan_raw, cudaStream_t st) {
+  constexpr int R = N / 32;
   const int xlen = (HW - 1) * hop + N;   // hop is even; the bulk path needs hop % 4 == 0, which keeps both slots 16-byte aligned
-  const size_t smem = sizeof(float2) * (HW * kFft16BufLen + kFft16TabLen + N / 2) + sizeof(float) * 2 * (size_t)xlen;
-  auto kern = stft512_hw_kernel<HW>;
+  const size_t smem = sizeof(float2) * (HW * fft16_buf_len<R>() + fft16_tab_len<R>() + N / 2) + sizeof(float) * 2 * (size_t)xlen;
+  auto kern = stft_hw_kernel<N, HW, MINB>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int per_sm = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, HW * 16, smem);
@@ -421,10 +428,14 @@ int k_stft(const float *x, long long row_pitch, int rows, int M, int T, int N, i
     case 256: return launch_stft<256>(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, chan_raw, st);
     case 512: {
       static const bool stockham = getenv("MCAG_STFT_STOCKHAM") != nullptr;
-      if (!stockham) return launch_stft512_hw(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, chan_raw, st);
+      if (!stockham) return launch_stft_hw<512, MCAG_STFT512_HW, MCAG_STFT512_MINB>(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, chan_raw, st);
       return launch_stft<512>(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, chan_raw, st);
     }
-    case 1024: return launch_stft<1024>(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, chan_raw, st);
+    case 1024: {
+      static const bool stockham = getenv("MCAG_STFT_STOCKHAM") != nullptr;
+      if (!stockham) return launch_stft_hw<1024, MCAG_STFT1024_HW, MCAG_STFT1024_MINB>(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, chan_raw, st);
+      return launch_stft<1024>(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, chan_raw, st);
+    }
     case 2048: return launch_stft<2048>(x, row_pitch, rows, M, T, hop, win, tw, spec, chan_pow, chan_raw, st);
   }
   return mcag_set_error(1, "stft: frame size must be 256, 512, 1024 or 2048");
