@@ -20,10 +20,10 @@ cap() {  # workload, kernel regex, skip, count, tag
     python bench.py --workload $1 --steps 2 --warmup 3 --no-e2e $B > /dev/null 2>&1
 }
 cap cfg2 stft_tdoa_warp_kernel 3 1 cfg2_stft_tdoa
-cap cfg5 "srp_tc_small_kernel|ds_select_kernel|stft_kernel" 9 3 cfg5_srp
+cap cfg5 "srp_tc_small_kernel|ds_select_kernel|stft_hw_kernel" 9 3 cfg5_srp
 cap cfg4 "srp_tc_kernel|srp_prepare_kernel" 6 2 cfg4_srp_tc
 cap cfg3 "ds_fan_tc_kernel" 3 1 cfg3_ds_fan
 cap cfg1m "mask_fused_kernel" 3 1 cfg1m_fused
 cap cfg1b "mb_fused_kernel|mb_gate_kernel" 6 2 cfg1b_kernels
-cap cfg1l "gcc_tau_tc_kernel|curve_scan|stft_kernel" 9 3 cfg1l_kernels
+cap cfg1l "gcc_tau_tc_kernel|curve_scan|stft_hw_kernel" 9 3 cfg1l_kernels
 ls -la $O | grep "${R}_" | tail -40

@@ -11,6 +11,10 @@ xyz16 = scenes.linear_array((np.arange(16) - 7.5) * 0.035)
 x4 = scenes.far_field_scene(xyz4, fs, 6000, scenes.azimuth_dirs([0.5]), seed=1).astype(np.float32)
 x16 = scenes.far_field_scene(xyz16, fs, 6000, scenes.azimuth_dirs([0.5]), seed=2).astype(np.float32)
 x2 = scenes.far_field_scene(scenes.linear_array([0, 0.086]), fs, 6000, scenes.azimuth_dirs([0.5]), seed=3).astype(np.float32)
+xyz64 = scenes.planar_array(8, 8, 0.04)
+x64 = scenes.far_field_scene(xyz64, fs, 6000, scenes.az_el_dirs(np.array([[0.4]]), np.array([[0.6]])), seed=4).astype(np.float32)
+rng = np.random.default_rng(5)
+w_fs = rng.standard_normal((7, 16, 257)) + 1j * rng.standard_normal((7, 16, 257))
 for p, x in ((mb.SourceSeparationAndLocalisation(fs, xyz4, 1, usePowerFloor=False, max_frames_per_call=32), x4),
              (mb.SourceSeparationAndLocalisation(fs, xyz16, 2, usePowerFloor=True, max_frames_per_call=32), x16),
              (mb.SourceLocalisation(fs, xyz16, 1, usePowerFloor=False, max_frames_per_call=32), x16),
@@ -20,7 +24,10 @@ for p, x in ((mb.SourceSeparationAndLocalisation(fs, xyz4, 1, usePowerFloor=Fals
              (mb.TdoaEstimator(fs, 4, 1024, 20, max_frames_per_call=32, emit_curves=True), x4),
              (mb.TdoaEstimator(fs, 4, 256, 9, max_frames_per_call=64), x4),
              (mb.DelayAndSumFan(fs, xyz4, 2048, np.deg2rad(np.arange(-90, 91, 10.0)), max_frames_per_call=8), x4),
-             (mb.SrpPhat(fs, xyz16, 512, scenes.az_el_dirs(np.linspace(-3, 3, 50)[:, None], np.array([0.2, 0.9])[None, :]), max_frames_per_call=32), x16)):
+             (mb.SrpPhat(fs, xyz16, 512, scenes.az_el_dirs(np.linspace(-3, 3, 50)[:, None], np.array([0.2, 0.9])[None, :]), max_frames_per_call=32), x16),
+             (mb.SrpPhat(fs, xyz64, 1024, scenes.az_el_dirs(np.linspace(-3, 3, 40)[:, None], np.array([0.2, 0.9])[None, :]), max_frames_per_call=32), x64),   # srp_tc_kernel, stft_hw<1024>
+             (mb.DelayAndSumFan(fs, xyz16, 1024, np.deg2rad(np.arange(-90, 91, 5.0)), max_frames_per_call=32), x16),                                         # ds_fan_tc_kernel
+             (mb.FilterAndSumFan(fs, 16, 512, w_fs, max_frames_per_call=32), x16)):
     for pos in range(0, x.shape[1], 2500):
         p.process(x[:, pos:pos + 2500])
     p.synchronize(); p.close()
