@@ -13,9 +13,9 @@
 //   warp 0       MMA issuer: per 16-bin chunk 12 tcgen05.mma.kind::tf32 M128 N64 K8 into one of two 64-column TMEM accumulators
 //   warp 1       table loader: the delay operand is the same for every frame tile, so it is tabulated once per processor in the
 //                canonical swizzled K-major layout (gcc_tc_table_kernel) and fetched per chunk by one 16 KB bulk copy (TMA engine)
-//   warps 2-9    cross-spectrum producers: thread = (frame row, two bins): 16-byte loads of both channels with the BINS along the
+//   warps 2-17   cross-spectrum producers: thread = (two frame rows, two bins): 16-byte loads of both channels with the BINS along the
 //                lanes (eight lanes cover 128 contiguous bytes of a spectrum row), PHAT, 3xTF32 split, swizzled 16-byte stores
-//   warps 10-13  epilogue: tcgen05.ld the finished accumulator, store corr rows
+//   warps 18-21  epilogue: tcgen05.ld the finished accumulator, store corr rows
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -27,7 +27,9 @@ constexpr int GT2_A_BYTES = GT2_BM * GT2_KC * 4;   // 16 KB
 constexpr int GT2_B_BYTES = GT2_BD * GT2_KC * 4;   // 8 KB
 constexpr int GT2_STAGE_BYTES = 2 * GT2_A_BYTES + 2 * GT2_B_BYTES;   // 48 KB
 constexpr int GT2_SMEM = GT2_STAGES * GT2_STAGE_BYTES + 1024 + 256;
-constexpr int GT2_PROD_THREADS = 256, GT2_EPI_THREADS = 128, GT2_THREADS = 64 + GT2_PROD_THREADS + GT2_EPI_THREADS;
+// 16 producer warps: the operand build is a latency chain (load, whiten, store, fence, arrive) per chunk and warp; 8 warps ran cfg1l in
+// 0.41 ms, 16 in 0.35 ms, 4 in 0.62 ms
+constexpr int GT2_PROD_THREADS = 512, GT2_RPT = 128 * 8 / GT2_PROD_THREADS /* frame rows per producer thread */, GT2_EPI_THREADS = 128, GT2_THREADS = 64 + GT2_PROD_THREADS + GT2_EPI_THREADS;
 constexpr uint32_t GT2_IDESC = umma_idesc_tf32(128, 64);
 
 __host__ __device__ constexpr int gt2_chunks(int N) { return (N + 2 + GT2_KC - 1) / GT2_KC; }   // 2K = N + 2 floats deep
@@ -142,10 +144,10 @@ __global__ void __launch_bounds__(GT2_THREADS, 1) gcc_tau_tc_kernel(const Gt2Par
       for (int c = 0; c < p.NCH; ++c) {
         const int k0 = c * 16 + 2 * q;
         const bool inrow = k0 < p.KP;   // KP is even: a 16-byte unit is inside the row or entirely past it
-        float4 l[4], r[4];
+        float4 l[GT2_RPT], r[GT2_RPT];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const long long t = (long long)tt * GT2_BM + r0 + 32 * i;
+        for (int i = 0; i < GT2_RPT; ++i) {
+          const long long t = (long long)tt * GT2_BM + r0 + (GT2_PROD_THREADS / 8) * i;
           const bool ok = inrow && t < p.BT;
           const float2 *row = p.spec + (ok ? t : 0) * p.M * p.KP + (ok ? k0 : 0);
           l[i] = __ldg(reinterpret_cast<const float4 *>(row + (size_t)mi * p.KP));
@@ -155,8 +157,8 @@ __global__ void __launch_bounds__(GT2_THREADS, 1) gcc_tau_tc_kernel(const Gt2Par
         mbar_wait_bounded(&empty[stage], phase ^ 1);
         unsigned char *st = smem + stage * GT2_STAGE_BYTES;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int row = r0 + 32 * i;
+        for (int i = 0; i < GT2_RPT; ++i) {
+          const int row = r0 + (GT2_PROD_THREADS / 8) * i;
           float2 g0 = whiten(cmulc(make_float2(l[i].x, l[i].y), make_float2(r[i].x, r[i].y)));
           float2 g1 = whiten(cmulc(make_float2(l[i].z, l[i].w), make_float2(r[i].z, r[i].w)));
           if (k0 >= p.K) g0 = make_float2(0.f, 0.f);        // the pad bin never contributes
