@@ -75,6 +75,46 @@ def test_stft_istft_parity(mb, orc, N, path):
     assert np.allclose(p.power_db()[0], orc.fft_log_power(S, N), rtol=0, atol=1e-3)
 
 
+@pytest.mark.parametrize("N,hop,T,M,offset", [(512, 256, 13, 3, 0), (512, 128, 29, 2, 0), (512, 256, 7, 2, 1), (512, 64, 40, 1, 0),
+                                              (1024, 512, 13, 3, 0), (1024, 256, 21, 2, 0), (1024, 512, 5, 2, 2), (1024, 1024, 9, 1, 0),
+                                              (256, 128, 11, 2, 0), (2048, 1024, 6, 2, 0)])
+def test_stft_kernel_shapes(mb, N, hop, T, M, offset):
+    """mcag_k_stft on its own against numpy float64: the half-warp engine (N = 512 / 1024) and the Stockham engine (256 / 2048) with
+    frame counts that leave a half-filled last work item (the idle half-warp of a warp), several hops, and sample rows that are not
+    16-byte aligned (offset in floats: the element-wise staging path instead of the bulk copy); Parseval power beside it."""
+    import ctypes as C
+    import torch
+    from mcarray_b200 import capi
+    lib = capi.lib()
+    rng = np.random.default_rng(N + hop + T)
+    rows, n = 2 * M, (T - 1) * hop + N
+    pitch = n + 8
+    xh = (rng.standard_normal((rows, pitch)) * 2000).astype(np.float32)
+    win = np.sqrt(0.5 - 0.5 * np.cos(2 * np.pi * np.arange(N) / N)).astype(np.float32)
+    buf = torch.zeros(rows * pitch + 8, device="cuda")
+    x = buf[offset:offset + rows * pitch]
+    x.copy_(torch.from_numpy(xh.reshape(-1)))
+    dwin = torch.from_numpy(win).cuda()
+    tw = torch.empty(lib.mcag_k_twiddle_count(N), 2, device="cuda")
+    capi.check(lib.mcag_k_twiddles(N, capi.vp(tw), None))
+    KP = N // 2 + 2
+    spec = torch.full((2, T, M, KP, 2), 7.0, device="cuda")
+    pw = torch.zeros(2, T, M, device="cuda")
+    torch.cuda.synchronize()
+    capi.check(lib.mcag_k_stft(capi.vp(x), C.c_longlong(pitch), rows, M, T, N, hop, capi.vp(dwin), capi.vp(tw), capi.vp(spec), capi.vp(pw), None))
+    torch.cuda.synchronize()
+    got = spec.cpu().numpy()
+    got = got[..., 0] + 1j * got[..., 1]
+    frames = np.stack([xh[:, t * hop:t * hop + N].astype(np.float64) * win.astype(np.float64) for t in range(T)], axis=1)   # [rows][T][N]
+    ref = np.fft.rfft(frames, axis=2).reshape(2, M, T, N // 2 + 1).transpose(0, 2, 1, 3)                                    # [B][T][M][K]
+    assert np.all(got[..., N // 2 + 1] == 0)                                                                                # the pad bin
+    assert_close(got[..., :N // 2 + 1].reshape(2 * T, M, -1), ref.reshape(2 * T, M, -1), (1, 2), f"stft kernel N={N} hop={hop}")
+    k = np.arange(N // 2 + 1)
+    wk = np.where((k == 0) | (k == N // 2), 1.0, 2.0)
+    pref = (np.abs(ref) ** 2 * wk).sum(axis=3) / (N * N)
+    np.testing.assert_allclose(pw.cpu().numpy(), pref, rtol=2e-5)
+
+
 def test_tdoa_config2_parity(mb, orc):
     """BASELINE config 2: 8-mic circular array r = 0.10 m, 48 kHz, N = 1024, 28 pairs, lag window +-28."""
     fs, N, L = 48000, 1024, 28
