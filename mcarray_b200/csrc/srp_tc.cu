@@ -592,12 +592,23 @@ static void tc_plan(long long BT, int M, int N, int D, TcParams &p, long long &B
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   p.BT = BT; p.D = D; p.M = M; p.K = K;
   p.n_tt = (int)(BTpad / TC_BM); p.n_dt = (D + TC_BD - 1) / TC_BD;
-  // bin ranges: enough work items for ~4 waves of persistent CTAs, at least 16 bins each
+  // bin ranges: 3 to 8 waves of work items for the persistent CTAs (one per SM), at least 16 bins each; among those the count that
+  // leaves the last wave fullest (cfg4 on one GPU: 232 tiles x 3 ranges = 4.7 waves, x 5 = 7.8; the sharded grid at 8 GPUs: 32 tiles x
+  // 19 ranges = 4.1 waves, a fifth wave one ninth full, x 18 = 3.9)
   const long long tiles = (long long)p.n_tt * p.n_dt;
-  int n_ks = (int)((4LL * sms + tiles - 1) / tiles);
-  if (n_ks > K / 16) n_ks = K / 16;
-  if (n_ks < 1) n_ks = 1;
-  p.bins_per_range = (K + n_ks - 1) / n_ks;
+  const int n_max = K / 16 > 0 ? K / 16 : 1;
+  int best = (int)((4LL * sms + tiles - 1) / tiles);   // small problems (never 3 waves): as many ranges as it takes to reach ~4 waves, capped
+  if (best > n_max) best = n_max;
+  if (best < 1) best = 1;
+  double best_eff = -1.0;
+  for (int n = 1; n <= n_max; ++n) {
+    const int bpr = (K + n - 1) / n, nn = (K + bpr - 1) / bpr;   // the count the rounding of bins_per_range really gives
+    const long long items = tiles * nn, waves = (items + sms - 1) / sms;
+    if (waves < 3 || waves > 8) continue;
+    const double eff = (double)items / (double)(waves * sms);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = n; }
+  }
+  p.bins_per_range = (K + best - 1) / best;
   p.n_ks = (K + p.bins_per_range - 1) / p.bins_per_range;
 }
 bool k_srp_tensor_supported(int M) { return M % 16 == 0 && M >= 16 && M <= 64; }
