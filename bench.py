@@ -57,6 +57,24 @@ def measured_peaks():
 # workloads
 # ----------------------------------------------------------------------------------------------------------------------
 class Workload:
+    result_what = None   # MCAG_OUT_* id of the per-step result the e2e leg reads back (None: the audio the call itself returns)
+
+    def fetch_bytes(self, p, B, T):
+        return self.result_bytes(p, B, T)
+
+    def fetch_result(self, p):
+        """the step's result into a pinned host buffer kept across steps (a fresh pageable array per step costs page faults and a staged copy:
+        0.4 ms for cfg2's 5.4 MB of lags, 150 ms for cfg3's 760 MB of beams)"""
+        if self.result_what is None:
+            return None
+        import torch
+        from mcarray_b200 import capi
+        nbytes = self.fetch_bytes(p, p.info.n_streams, p.frames_done)
+        if getattr(self, "_pin", None) is None or self._pin.numel() < nbytes:
+            self._pin = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        capi.check(capi.lib().mcag_fetch(p.handle, self.result_what, C.c_void_p(self._pin.data_ptr()), C.c_longlong(nbytes)))
+        return self._pin
+
     name = ""
 
     def scene(self, stream_id, n):
@@ -100,8 +118,7 @@ class Cfg2(Workload):
     def result_bytes(self, p, B, T):
         return B * T * p.info.n_pairs * 4
 
-    def fetch_result(self, p):
-        return p.lags()
+    result_what = 6   # MCAG_OUT_LAGS
 
     # algorithmic (compulsory) HBM bytes per frame per stream for each kernel of the chain, fp32
     def kernel_bytes_per_frame(self):
@@ -138,8 +155,10 @@ class Cfg5(Workload):
     def result_bytes(self, p, B, T):
         return B * T * 4 + B * T * self.hop * 4
 
-    def fetch_result(self, p):
-        return p.cells()
+    def fetch_bytes(self, p, B, T):
+        return B * T * 4            # the cells; the audio comes back through the call itself
+
+    result_what = 4   # MCAG_OUT_CELL
 
     def kernel_bytes_per_frame(self):
         M, hop, K, P, D = self.M, self.hop, self.N // 2 + 1, self.M * (self.M - 1) // 2, 37
@@ -196,8 +215,7 @@ class Cfg4(Workload):
     def result_bytes(self, p, B, T):
         return B * T * 4
 
-    def fetch_result(self, p):
-        return p.cells()
+    result_what = 4   # MCAG_OUT_CELL
 
     def kernel_bytes_per_frame(self):
         M, hop, K, D = self.M, self.hop, self.N // 2 + 1, self.D
@@ -230,8 +248,7 @@ class Cfg4Sharded(Cfg4):
     def host_input(self, rank, B, n, unique=8):
         return super().host_input(0, B, n, unique)                  # every rank sees the same array signals
 
-    def fetch_result(self, p):
-        return None
+    result_what = None
 
 
 def _threaded(fn, items, n_threads):
@@ -265,8 +282,7 @@ class Cfg1Mask(Workload):
     def result_bytes(self, p, B, T):
         return B * 2 * T * self.hop * 4
 
-    def fetch_result(self, p):
-        return None
+    result_what = None
 
     def kernel_bytes_per_frame(self):
         K, hop, nb = self.N // 2 + 1, self.hop, 45
@@ -299,8 +315,7 @@ class Cfg1Loc(Workload):
     def result_bytes(self, p, B, T):
         return B * T * 4
 
-    def fetch_result(self, p):
-        return p.cells()
+    result_what = 4   # MCAG_OUT_CELL
 
     def kernel_bytes_per_frame(self):
         K, hop, D = self.N // 2 + 1, self.hop, 61
@@ -354,15 +369,7 @@ class Cfg3(Workload):
     def result_bytes(self, p, B, T):
         return B * T * self.D * p.info.spectrum_pitch * 8
 
-    def fetch_result(self, p):
-        # MCAG_OUT_BEAMS (760 MB per step) into a pinned buffer kept across steps: a fresh pageable array per step cost 150 ms
-        import torch
-        from mcarray_b200 import capi
-        nbytes = self.result_bytes(p, p.info.n_streams, p.frames_done)
-        if getattr(self, "_pin", None) is None or self._pin.numel() < nbytes:
-            self._pin = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
-        capi.check(capi.lib().mcag_fetch(p.handle, 9, C.c_void_p(self._pin.data_ptr()), C.c_longlong(nbytes)))
-        return self._pin
+    result_what = 9   # MCAG_OUT_BEAMS, 760 MB per step
 
     def kernel_bytes_per_frame(self):
         M, hop, K, D = self.M, self.hop, self.N // 2 + 1, self.D

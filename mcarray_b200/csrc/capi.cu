@@ -181,7 +181,7 @@ struct mcag_proc_s {
   int rows;
   int srp_form = 0;   // SSL / SL: 1 pair form, 2 channel form on the tensor cores (mcag_config::srp_form resolved at create)
   cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
-  cudaEvent_t ev_in[8] = {nullptr}, ev_done[8] = {nullptr};
+  cudaEvent_t ev_in[16] = {nullptr}, ev_done[16] = {nullptr};
   long long launches = 0, frames_total = 0;
   int frames_last = 0;
   // input FIFO (ping-pong), per row capacity fifo_cap floats, fill = carried samples (same for every row)
@@ -320,7 +320,7 @@ int mcag_create(const mcag_config *cfg, mcag_proc *out) {
   if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(mcag_set_error(MCAG_ERR_CUDA, "stream creation failed"));
   if (cudaStreamCreateWithFlags(&p->copy_in, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&p->copy_out, cudaStreamNonBlocking) != cudaSuccess)
     return fail(mcag_set_error(MCAG_ERR_CUDA, "stream creation failed"));
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 16; ++i)
     if (cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&p->ev_done[i], cudaEventDisableTiming) != cudaSuccess)
       return fail(mcag_set_error(MCAG_ERR_CUDA, "event creation failed"));
   cudaStream_t st = p->stream;
@@ -540,7 +540,7 @@ void mcag_destroy(mcag_proc p) {
   for (cudaEvent_t e : p->prof_pool) cudaEventDestroy(e);
   if (p->pin_in) cudaFreeHost(p->pin_in);
   if (p->pin_out) cudaFreeHost(p->pin_out);
-  for (int i = 0; i < 8; ++i) { if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]); if (p->ev_done[i]) cudaEventDestroy(p->ev_done[i]); }
+  for (int i = 0; i < 16; ++i) { if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]); if (p->ev_done[i]) cudaEventDestroy(p->ev_done[i]); }
   if (p->copy_in) cudaStreamDestroy(p->copy_in);
   if (p->copy_out) cudaStreamDestroy(p->copy_out);
   if (p->stream) cudaStreamDestroy(p->stream);
@@ -945,7 +945,10 @@ __global__ void convert_out_kernel(const float *__restrict__ in, Tout *__restric
   if (i < n) out[i] = narrow_sample<Tout>(in[i]);
 }
 
-constexpr int kMaxChunks = 8;
+#ifndef MCAG_MAX_CHUNKS
+#define MCAG_MAX_CHUNKS 8
+#endif
+constexpr int kMaxChunks = MCAG_MAX_CHUNKS;
 
 // Host-buffer process call.  The streams of the handle are cut into up to kMaxChunks groups; group c+1 is copied host->device
 // on the copy-in stream while the kernels of group c run on the compute stream, and the audio of group c goes back on the
@@ -987,7 +990,9 @@ static int process_host(mcag_proc p, const Tio *const *in, const Tio *in_packed,
       else for (int r = r0; r < r1; ++r) CU(cudaMemcpyAsync(cur + (long long)r * p->fifo_cap + p->fill, in[r], (size_t)nsamples * 4, cudaMemcpyHostToDevice, sin));
     } else {
       Tio *dst = p->stage_in.as<Tio>() + (long long)r0 * nsamples;
-      if (in_packed) CU(cudaMemcpy2DAsync(dst, (size_t)nsamples * sizeof(Tio), in_packed + (long long)r0 * in_pitch, in_pitch * sizeof(Tio), (size_t)nsamples * sizeof(Tio), r1 - r0, cudaMemcpyHostToDevice, sin));
+      if (in_packed && in_pitch == nsamples)   // dense on both sides: one linear copy (the 2-D form of the same bytes ran below the pinned-copy rate)
+        CU(cudaMemcpyAsync(dst, in_packed + (long long)r0 * in_pitch, (size_t)(r1 - r0) * nsamples * sizeof(Tio), cudaMemcpyHostToDevice, sin));
+      else if (in_packed) CU(cudaMemcpy2DAsync(dst, (size_t)nsamples * sizeof(Tio), in_packed + (long long)r0 * in_pitch, in_pitch * sizeof(Tio), (size_t)nsamples * sizeof(Tio), r1 - r0, cudaMemcpyHostToDevice, sin));
       else for (int r = r0; r < r1; ++r) CU(cudaMemcpyAsync(p->stage_in.as<Tio>() + (long long)r * nsamples, in[r], (size_t)nsamples * sizeof(Tio), cudaMemcpyHostToDevice, sin));
     }
     CU(cudaEventRecord(p->ev_in[c], sin));
