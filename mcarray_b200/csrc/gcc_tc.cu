@@ -136,41 +136,64 @@ __global__ void __launch_bounds__(GT2_THREADS, 1) gcc_tau_tc_kernel(const Gt2Par
     const int g = tid - 64;
     const int q = g & 7, r0 = g >> 3;   // 16-byte unit (two bins) of the chunk; frame rows r0, r0 + 32, r0 + 64, r0 + 96 of the tile
     int stage = 0; uint32_t phase = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int pr = item % p.P, tt = item / p.P;
-      int mi = 0, rem = pr;   // pair -> (i, j), i < j lexicographic (SteeringBeamforming.cpp:63-65)
+    auto decode = [&](int item, int &tt, int &mi, int &mj) {   // pair -> (i, j), i < j lexicographic (SteeringBeamforming.cpp:63-65)
+      int rem = item % p.P;
+      tt = item / p.P; mi = 0;
       while (rem >= p.M - 1 - mi) { rem -= p.M - 1 - mi; ++mi; }
-      const int mj = mi + 1 + rem;
-      for (int c = 0; c < p.NCH; ++c) {
-        const int k0 = c * 16 + 2 * q;
-        const bool inrow = k0 < p.KP;   // KP is even: a 16-byte unit is inside the row or entirely past it
-        float4 l[GT2_RPT], r[GT2_RPT];
+      mj = mi + 1 + rem;
+    };
+    // always a load (rows past the last frame and units past the row end read frame 0 / unit 0 and are zeroed when they are USED): a select
+    // against zero right behind the load would make the prefetch wait for its own data
+    auto load_chunk = [&](int tt, int mi, int mj, int c, float4 (&l)[GT2_RPT], float4 (&r)[GT2_RPT]) {
+      const int k0 = c * 16 + 2 * q;
+      const bool inrow = k0 < p.KP;   // KP is even: a 16-byte unit is inside the row or entirely past it
 #pragma unroll
-        for (int i = 0; i < GT2_RPT; ++i) {
-          const long long t = (long long)tt * GT2_BM + r0 + (GT2_PROD_THREADS / 8) * i;
-          const bool ok = inrow && t < p.BT;
-          const float2 *row = p.spec + (ok ? t : 0) * p.M * p.KP + (ok ? k0 : 0);
-          l[i] = __ldg(reinterpret_cast<const float4 *>(row + (size_t)mi * p.KP));
-          r[i] = __ldg(reinterpret_cast<const float4 *>(row + (size_t)mj * p.KP));
-          if (!ok) { l[i] = make_float4(0.f, 0.f, 0.f, 0.f); r[i] = l[i]; }
-        }
-        mbar_wait_bounded(&empty[stage], phase ^ 1);
-        unsigned char *st = smem + stage * GT2_STAGE_BYTES;
+      for (int i = 0; i < GT2_RPT; ++i) {
+        const long long t = (long long)tt * GT2_BM + r0 + (GT2_PROD_THREADS / 8) * i;
+        const bool ok = inrow && t < p.BT;
+        const float2 *row = p.spec + (ok ? t : 0) * p.M * p.KP + (ok ? k0 : 0);
+        l[i] = __ldg(reinterpret_cast<const float4 *>(row + (size_t)mi * p.KP));
+        r[i] = __ldg(reinterpret_cast<const float4 *>(row + (size_t)mj * p.KP));
+      }
+    };
+    // The spectra of the NEXT chunk (or of the next item's first chunk) are requested before the current chunk is whitened and stored
+    int item = blockIdx.x;
+    if (item < n_items) {
+      int tt, mi, mj;
+      decode(item, tt, mi, mj);
+      float4 l[GT2_RPT], r[GT2_RPT], nl[GT2_RPT], nr[GT2_RPT];
+      load_chunk(tt, mi, mj, 0, l, r);
+      while (item < n_items) {
+        const int nitem = item + gridDim.x;
+        int ntt = 0, nmi = 0, nmj = 1;
+        if (nitem < n_items) decode(nitem, ntt, nmi, nmj);
+        for (int c = 0; c < p.NCH; ++c) {
+          if (c + 1 < p.NCH) load_chunk(tt, mi, mj, c + 1, nl, nr);
+          else if (nitem < n_items) load_chunk(ntt, nmi, nmj, 0, nl, nr);
+          const int k0 = c * 16 + 2 * q;
+          const bool inrow = k0 < p.KP;
+          mbar_wait_bounded(&empty[stage], phase ^ 1);
+          unsigned char *st = smem + stage * GT2_STAGE_BYTES;
 #pragma unroll
-        for (int i = 0; i < GT2_RPT; ++i) {
-          const int row = r0 + (GT2_PROD_THREADS / 8) * i;
-          float2 g0 = whiten(cmulc(make_float2(l[i].x, l[i].y), make_float2(r[i].x, r[i].y)));
-          float2 g1 = whiten(cmulc(make_float2(l[i].z, l[i].w), make_float2(r[i].z, r[i].w)));
-          if (k0 >= p.K) g0 = make_float2(0.f, 0.f);        // the pad bin never contributes
-          if (k0 + 1 >= p.K) g1 = make_float2(0.f, 0.f);
-          const float h0 = tf32_hi(g0.x), h1 = tf32_hi(g0.y), h2 = tf32_hi(g1.x), h3 = tf32_hi(g1.y);
-          const uint32_t off = (uint32_t)row * 128u + (((uint32_t)q ^ (uint32_t)(row & 7)) << 4);
-          *reinterpret_cast<float4 *>(st + off) = make_float4(h0, h1, h2, h3);
-          *reinterpret_cast<float4 *>(st + GT2_A_BYTES + off) = make_float4(g0.x - h0, g0.y - h1, g1.x - h2, g1.y - h3);
+          for (int i = 0; i < GT2_RPT; ++i) {
+            const int row = r0 + (GT2_PROD_THREADS / 8) * i;
+            const bool ok = inrow && (long long)tt * GT2_BM + row < p.BT;
+            float2 g0 = whiten(cmulc(make_float2(l[i].x, l[i].y), make_float2(r[i].x, r[i].y)));
+            float2 g1 = whiten(cmulc(make_float2(l[i].z, l[i].w), make_float2(r[i].z, r[i].w)));
+            if (!ok || k0 >= p.K) g0 = make_float2(0.f, 0.f);        // the pad bin never contributes
+            if (!ok || k0 + 1 >= p.K) g1 = make_float2(0.f, 0.f);
+            const float h0 = tf32_hi(g0.x), h1 = tf32_hi(g0.y), h2 = tf32_hi(g1.x), h3 = tf32_hi(g1.y);
+            const uint32_t off = (uint32_t)row * 128u + (((uint32_t)q ^ (uint32_t)(row & 7)) << 4);
+            *reinterpret_cast<float4 *>(st + off) = make_float4(h0, h1, h2, h3);
+            *reinterpret_cast<float4 *>(st + GT2_A_BYTES + off) = make_float4(g0.x - h0, g0.y - h1, g1.x - h2, g1.y - h3);
+          }
+          fence_async_smem();
+          mbar_arrive_warp(&full_a[stage]);
+          if (++stage == GT2_STAGES) { stage = 0; phase ^= 1; }
+#pragma unroll
+          for (int i = 0; i < GT2_RPT; ++i) { l[i] = nl[i]; r[i] = nr[i]; }
         }
-        fence_async_smem();
-        mbar_arrive_warp(&full_a[stage]);
-        if (++stage == GT2_STAGES) { stage = 0; phase ^= 1; }
+        item = nitem; tt = ntt; mi = nmi; mj = nmj;
       }
     }
   } else {
