@@ -4,15 +4,15 @@
 // times (three radix passes) and once more for the real post-processing: 197 shared-memory wavefronts per frame, and ncu shows the STFT
 // and the fused masking kernel bound by exactly that (r2_cfg1l_kernels: l1tex data-pipe 76 % of peak at 39 % of the DRAM peak).  Here a
 // transform belongs to SIXTEEN lanes holding sixteen points each (thirty-two for N = 1024): 256 = 16 x 16 (512 = 32 x 16), so both
-// passes run in registers (all their twiddles are immediates), the only exchange is ONE swizzled transpose through shared memory, and the real post-processing
-// pairs bin k with bin 256 - k, which live in lane c and lane 16 - c of the same half-warp: a shuffle, not a round trip.  A warp carries
-// two transforms (two frames of a row); nothing wider than __syncwarp is needed.
+// passes run in registers (all their twiddles are immediates), the only exchange is ONE swizzled transpose through shared memory, and
+// the real post-processing pairs bin k with bin N/2 - k, which live in lane c and lane 16 - c of the same half-warp: a shuffle, not a
+// round trip.  A warp carries two transforms (two frames of a row); nothing wider than __syncwarp is needed.
 //
-//   forward   lane b holds z[16 a + b] (a = register)  -> dft16 over a -> * W256^(b c) -> transpose -> dft16 over b -> Z[c + 16 d] in lane c
-//   inverse   the same schedule with conjugated twiddles takes Z[c + 16 d] in lane c back to z[16 a + b] in lane b (unscaled)
+//   forward   lane b holds z[16 a + b] (a = register) -> dft16 / dft32 over a -> * W^(b c) -> transpose -> dft16 over b -> Z[c + 16 e] in lane c
+//   inverse   the same schedule with conjugated twiddles takes Z[c + 16 e] in lane c back to z[16 a + b] in lane b (unscaled)
 //
 // Checked against numpy in tools/proto/fft16_halfwarp.py (index maps, lane pairing, bank-conflict freedom of the transpose, and the inverse
-// pre-processing).  Used by stft512_hw_kernel.  A one-warp-per-stream FastBinauralMasking kernel on this engine (left / right channel in
+// pre-processing).  Used by stft_hw_kernel (stft.cu).  A one-warp-per-stream FastBinauralMasking kernel on this engine (left / right channel in
 // the two half-warps, spectra held in registers from analysis to synthesis) was built and measured in round 2: 640 shared-memory
 // wavefronts per stereo frame against 1090, but 1.56 ms per cfg1m step against 1.29 ms for mask_fused_kernel - one warp per stream is
 // 14 warps per SM running a 4300-instruction loop body (68 KB of SASS, past the 32 KB L1.5 instruction cache: the no-instruction stall
@@ -105,14 +105,10 @@ template <bool INV> __device__ __forceinline__ void dft32(float2 (&x)[32]) {
 // R = points per lane: 16 (256-point packed-complex transform, N = 512) or 32 (512 points, N = 1024); sixteen lanes per transform
 template <int R> constexpr int fft16_tab_len() { return R * 16; }   // float2 entries of the inter-pass table: t1[c * 16 + b] = exp(-2 pi i b c / (16 R))
 template <int R> constexpr int fft16_buf_len() { return R * 16; }   // float2 entries of one transform's transpose buffer
-constexpr int kFft16TabLen = fft16_tab_len<16>(), kFft16BufLen = fft16_buf_len<16>();
 
 // builds the inter-pass table from the table of mcag_k_twiddles for N = 32 R (tw[n] = exp(-2 pi i n / N), n < N/2); the caller syncs
 template <int R> __device__ __forceinline__ void fft16_load_table(float2 *s_t1, const float2 *__restrict__ tw, int tid, int nthreads) {
   for (int i = tid; i < R * 16; i += nthreads) s_t1[i] = tw_lookup<false>(tw, 2 * (i >> 4) * (i & 15), 16 * R);
-}
-__device__ __forceinline__ void fft16_load_table(float2 *s_t1, const float2 *__restrict__ tw512, int tid, int nthreads) {
-  fft16_load_table<16>(s_t1, tw512, tid, nthreads);
 }
 
 // 16 R-point complex transform of one half-warp (l16 = lane & 15), in place in the registers: on entry v[a] = z[16 a + l16], on exit
@@ -142,7 +138,6 @@ template <int R, bool INV> __device__ __forceinline__ void fft_hw(float2 (&v)[R]
   }
   __syncwarp();   // the buffer may be rewritten by the next transform
 }
-template <bool INV> __device__ __forceinline__ void fft256_hw(float2 (&v)[16], float2 *xbuf, const float2 *s_t1, int l16) { fft_hw<16, INV>(v, xbuf, s_t1, l16); }
 
 // Real post-processing of an N = 32 R sample frame packed as z[n] = x[2n] + i x[2n+1]: on entry v[e] = Z[c + 16 e] (c = l16); emit(e, X) is
 // called with X[c + 16 e] for e = 0..R-1, and nyq = X[N/2] (real; meaningful on lane c = 0, whose X[0] has a zero imaginary part).
@@ -169,10 +164,6 @@ template <int R, class Emit> __device__ __forceinline__ void fft_hw_real_post(co
     emit(e, X);
   }
 }
-template <class Emit> __device__ __forceinline__ void fft16_real_post(const float2 (&v)[16], float2 wl, int l16, float &nyq, Emit emit) {
-  fft_hw_real_post<16>(v, wl, l16, nyq, emit);
-}
-
 // sum over the sixteen lanes of a half-warp, every lane gets it
 __device__ __forceinline__ float hw_sum(float x) {
 #pragma unroll
