@@ -367,7 +367,7 @@ class Cfg3(Workload):
         return mb.DelayAndSumFan(self.fs, self.xyz(), self.N, self.doas(), n_streams=B, max_frames_per_call=T)
 
     def result_bytes(self, p, B, T):
-        return B * T * self.D * p.info.spectrum_pitch * 8
+        return B * T * self.D * p.info.beams_pitch * 8
 
     result_what = 9   # MCAG_OUT_BEAMS, 760 MB per step
 

@@ -65,7 +65,7 @@ enum {
   MCAG_OUT_LAGS = 6,      /* int32  [B][T][P]         integer TDOA lags (TDOA)                    */
   MCAG_OUT_CURVES = 7,    /* float  [B][T][P][2L+1] (TDOA) or [B][T][D] smoothed curve (FREQGCC)  */
   MCAG_OUT_ACTIVE = 8,    /* uint8  [B][T]            1 where the power gate let the frame through */
-  MCAG_OUT_BEAMS = 9,     /* float2 [B][T][C][N/2+2]  beamformed / masked spectra (SSL, MASK, DSFAN: C = D) */
+  MCAG_OUT_BEAMS = 9,     /* float2 [B][T][C][mcag_info::beams_pitch]  beamformed / masked spectra (SSL, MASK: pitch N/2+2; DSFAN: C = D, rows padded) */
   MCAG_OUT_MASK_Q = 10,   /* float  [B][T][nb]        short-time band power after each frame (MASK) */
   MCAG_OUT_MASK_DEC = 11, /* uint8  [B][T][nb]        2 = spatial mask, 1 = temporal mask, 0 = pass (MASK) */
   MCAG_OUT_BAND_CELL = 12,/* int32  [B][T][nb]        arg-max cell of each sub-band curve (MULTIBAND); its MCAG_OUT_CURVES is [B][T][nb][D],
@@ -139,6 +139,8 @@ typedef struct {
   int frame_size, window_size, hop, analysis_length, one_sided_length, n_channels, n_streams, max_latency;
   int n_dirs, n_pairs, n_sources, n_out_channels, spectrum_pitch, max_frames_per_call;
   int srp_form;           /* SSL / SL: 1 = pair form, 2 = channel form (what mcag_create chose); 0 for other kinds */
+  int beams_pitch;        /* complex bins per row of MCAG_OUT_BEAMS: spectrum_pitch, except MCAG_KIND_DSFAN whose rows are padded to a multiple
+                             of 4 bins (32-byte aligned rows: the fan kernel writes them with 256-bit stores); the pad bins are zero */
 } mcag_info;
 
 const char *mcag_last_error(void);

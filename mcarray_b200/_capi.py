@@ -31,7 +31,7 @@ class Config(C.Structure):
 class Info(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "frame_size", "window_size", "hop", "analysis_length", "one_sided_length", "n_channels", "n_streams", "max_latency",
-        "n_dirs", "n_pairs", "n_sources", "n_out_channels", "spectrum_pitch", "max_frames_per_call", "srp_form")]
+        "n_dirs", "n_pairs", "n_sources", "n_out_channels", "spectrum_pitch", "max_frames_per_call", "srp_form", "beams_pitch")]
 
 
 _lib = None

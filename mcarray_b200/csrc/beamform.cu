@@ -67,9 +67,9 @@ int k_ds_select(const float2 *spec, int B, int T, int M, int N, const float2 *st
 constexpr int FAN_TF = 8, FAN_TD = 4, FAN_KC = 32;
 template <bool LOADED>
 __global__ void __launch_bounds__(256, 2) ds_fan_kernel(const float2 *__restrict__ spec, int T, int M, int N, const uint64_t *__restrict__ fx,
-                                                         const float2 *__restrict__ W, int D, float2 *__restrict__ out) {
+                                                         const float2 *__restrict__ W, int D, float2 *__restrict__ out, int KPo) {
   extern __shared__ float2 s_X[];   // [FAN_TF][M][FAN_KC]
-  const int KP = spec_pitch(N), K = N / 2 + 1;
+  const int KP = spec_pitch(N), K = N / 2 + 1;   // KPo >= KP: pitch of the output rows (bins K .. KPo - 1 are written as zeros)
   const int t0 = blockIdx.x * FAN_TF, k0 = blockIdx.y * FAN_KC, b = blockIdx.z;
   for (int i = threadIdx.x; i < FAN_TF * M * FAN_KC; i += blockDim.x) {
     const int kk = i % FAN_KC, c = (i / FAN_KC) % M, f = i / (FAN_KC * M);
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256, 2) ds_fan_kernel(const float2 *__restrict
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int k = k0 + lane;
-  if (k >= KP) return;   // no block-level synchronisation below
+  if (k >= KPo) return;   // no block-level synchronisation below
   const float invM = 1.0f / (float)M;
   for (int d0 = warp * FAN_TD; d0 < D; d0 += nwarp * FAN_TD) {
     float2 acc[FAN_TD][FAN_TF];
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256, 2) ds_fan_kernel(const float2 *__restrict
 #pragma unroll
       for (int i = 0; i < FAN_TD; ++i) {
         if constexpr (LOADED) {
-          a[i] = __ldg(W + ((size_t)min(d0 + i, D - 1) * M + c) * KP + k);                         // lanes = consecutive bins: 256-byte rows
+          a[i] = __ldg(W + ((size_t)min(d0 + i, D - 1) * M + c) * KP + min(k, KP - 1));                         // lanes = consecutive bins: 256-byte rows
         } else {
           const uint64_t f64 = __ldg(fx + (size_t)min(d0 + i, D - 1) * M + c);
           const int32_t ph = (int32_t)((uint32_t)((f64 + 0x80000000ull) >> 32) * (uint32_t)k);   // signed turns * 2^32, wraps exactly
@@ -115,32 +115,34 @@ __global__ void __launch_bounds__(256, 2) ds_fan_kernel(const float2 *__restrict
 #pragma unroll
       for (int f = 0; f < FAN_TF; ++f)
         if (t0 + f < T)
-          out[(((long long)b * T + t0 + f) * D + d0 + i) * KP + k] = (k < K) ? make_float2(acc[i][f].x * invM, acc[i][f].y * invM) : make_float2(0.f, 0.f);
+          out[(((long long)b * T + t0 + f) * D + d0 + i) * KPo + k] = (k < K) ? make_float2(acc[i][f].x * invM, acc[i][f].y * invM) : make_float2(0.f, 0.f);
     }
   }
 }
 
-int k_ds_fan(const float2 *spec, int B, int T, int M, int N, const uint64_t *steer_fx, int D, float2 *out, cudaStream_t st) {
+int k_ds_fan(const float2 *spec, int B, int T, int M, int N, const uint64_t *steer_fx, int D, float2 *out, cudaStream_t st, int out_pitch) {
   if (B <= 0 || T <= 0) return 0;
-  const int KP = spec_pitch(N);
+  const int KP = out_pitch > 0 ? out_pitch : spec_pitch(N);
+  if (KP < spec_pitch(N)) return mcag_set_error(1, "ds_fan: output pitch below the spectrum pitch");
   size_t smem = sizeof(float2) * FAN_TF * M * FAN_KC;
   if (smem > 200 * 1024) return mcag_set_error(1, "ds_fan: too many channels");
   cudaFuncSetAttribute(ds_fan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((T + FAN_TF - 1) / FAN_TF, (KP + FAN_KC - 1) / FAN_KC, B);
-  ds_fan_kernel<false><<<grid, 256, smem, st>>>(spec, T, M, N, steer_fx, nullptr, D, out);
+  ds_fan_kernel<false><<<grid, 256, smem, st>>>(spec, T, M, N, steer_fx, nullptr, D, out, KP);
   MCAG_CHECK_LAUNCH();
   return 0;
 }
 
 // filter-and-sum fan: weights [D][M][KP] float2 (pad bins ignored)
-int k_fs_fan(const float2 *spec, int B, int T, int M, int N, const float2 *weights, int D, float2 *out, cudaStream_t st) {
+int k_fs_fan(const float2 *spec, int B, int T, int M, int N, const float2 *weights, int D, float2 *out, cudaStream_t st, int out_pitch) {
   if (B <= 0 || T <= 0) return 0;
-  const int KP = spec_pitch(N);
+  const int KP = out_pitch > 0 ? out_pitch : spec_pitch(N);
+  if (KP < spec_pitch(N)) return mcag_set_error(1, "fs_fan: output pitch below the spectrum pitch");
   size_t smem = sizeof(float2) * FAN_TF * M * FAN_KC;
   if (smem > 200 * 1024) return mcag_set_error(1, "fs_fan: too many channels");
   cudaFuncSetAttribute(ds_fan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((T + FAN_TF - 1) / FAN_TF, (KP + FAN_KC - 1) / FAN_KC, B);
-  ds_fan_kernel<true><<<grid, 256, smem, st>>>(spec, T, M, N, nullptr, weights, D, out);
+  ds_fan_kernel<true><<<grid, 256, smem, st>>>(spec, T, M, N, nullptr, weights, D, out, KP);
   MCAG_CHECK_LAUNCH();
   return 0;
 }

@@ -456,7 +456,7 @@ int mcag_create(const mcag_config *cfg, mcag_proc *out) {
       if ((rc = upload(p->steer_tab, w.data(), w.size() * sizeof(float2), st))) return fail(rc);
       CUF(cudaStreamSynchronize(st));
     } else if ((rc = upload_fx(p->steer_fx, cfg->steer_turns, D * M, st))) return fail(rc);
-    if ((rc = p->beams.alloc(sizeof(float2) * B * T * D * KP))) return fail(rc);
+    if ((rc = p->beams.alloc(sizeof(float2) * B * T * D * fan_out_pitch(N)))) return fail(rc);   // rows padded to 32 bytes: 256-bit stores
   }
   if (kind == MCAG_KIND_SRP) {
     if (D < 3 || !cfg->mic_tau) return fail(mcag_set_error(MCAG_ERR_INVALID, "mic_tau [M][D] with D >= 3 required"));
@@ -564,6 +564,7 @@ int mcag_get_info(mcag_proc p, mcag_info *i) {
   i->frame_size = p->hop; i->window_size = p->N; i->hop = p->hop; i->analysis_length = p->N + 2; i->one_sided_length = p->K;
   i->n_channels = p->M; i->n_streams = p->B; i->max_latency = p->N; i->n_dirs = p->D; i->n_pairs = p->P; i->n_sources = p->S;
   i->n_out_channels = p->Cout; i->spectrum_pitch = p->KP; i->max_frames_per_call = p->Tmax; i->srp_form = p->srp_form;
+  i->beams_pitch = p->cfg.kind == MCAG_KIND_DSFAN ? fan_out_pitch(p->cfg.frame_size) : p->KP;
   return MCAG_OK;
 }
 
@@ -813,11 +814,11 @@ static int run_frames(mcag_proc p, const float *x_all, long long pitch, int T, i
     // 16 / 32 / 48 / 64 microphones: the contraction runs on the tensor cores with four consecutive bins of a tile resident in TMEM
     // (fan_tc.cu); other counts take the CUDA-core register-tile kernel.  MCAG_FAN_CUDA_CORES=1 forces the latter (tests compare the two).
     if (p->cfg.fs_weights)
-      OK(k_fs_fan(spec, B, T, M, N, p->steer_tab.as<float2>(), D, p->beams.as<float2>() + o * T * D * KP, st));
+      OK(k_fs_fan(spec, B, T, M, N, p->steer_tab.as<float2>(), D, p->beams.as<float2>() + o * T * D * fan_out_pitch(N), st, fan_out_pitch(N)));
     else if (k_ds_fan_tensor_supported(M) && !getenv("MCAG_FAN_CUDA_CORES"))
-      OK(k_ds_fan_tensor(spec, B, T, M, N, p->steer_fx.as<uint64_t>(), D, p->beams.as<float2>() + o * T * D * KP, st));
+      OK(k_ds_fan_tensor(spec, B, T, M, N, p->steer_fx.as<uint64_t>(), D, p->beams.as<float2>() + o * T * D * fan_out_pitch(N), st, fan_out_pitch(N)));
     else
-      OK(k_ds_fan(spec, B, T, M, N, p->steer_fx.as<uint64_t>(), D, p->beams.as<float2>() + o * T * D * KP, st));
+      OK(k_ds_fan(spec, B, T, M, N, p->steer_fx.as<uint64_t>(), D, p->beams.as<float2>() + o * T * D * fan_out_pitch(N), st, fan_out_pitch(N)));
     p->launches++;
   } else if (kind == MCAG_KIND_SRP) {
     {

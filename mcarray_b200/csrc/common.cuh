@@ -124,4 +124,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                : "memory");
 }
 
+// one 256-bit store (sm_100: STG.E.256); the address must be 32-byte aligned
+__device__ __forceinline__ void st_global_v8(void *p, float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a0), "f"(a1), "f"(a2), "f"(a3), "f"(a4), "f"(a5), "f"(a6), "f"(a7)
+               : "memory");
+}
+
 }  // namespace mcag

@@ -34,6 +34,7 @@ struct FtParams {
   float2 *beams;          // [BT][D][KP]
   long long BT;
   int D, M, K, KP;
+  int KPo, wide;          // pitch of the beam rows (complex bins); wide: rows and bin groups are 32-byte aligned -> one 256-bit store per row
   int n_tt, n_dt, n_kg;   // frame tiles, direction tiles, bin groups
   const uint64_t *steer_fx;   // [D][M] 0.64 fixed-point turns per bin
   float out_scale;        // 1 / M
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ds_fan_tc_kernel(const FtParams
       const bool second = k0 + 2 < p.KP;
       const int d = dt * FT_BD + quarter * 16 + (lane >> 1);
       const bool store = d < p.D && (!odd || second);
-      float2 *col = p.beams + (size_t)d * p.KP + k0 + (odd ? 2 : 0);   // + t * D * KP per frame
+      float2 *col = p.beams + (size_t)d * p.KPo + k0 + ((odd && !p.wide) ? 2 : 0);   // + t * D * KPo per frame
       mbar_wait_bounded(tmem_full, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(fh * 64);
@@ -231,15 +232,39 @@ __global__ void __launch_bounds__(FT_THREADS, 1) ds_fan_tc_kernel(const FtParams
 #pragma unroll
         for (int b = 0; b < FT_NB; ++b) tmem_ld8_nowait(taddr + b * 128 + j * 8, r[b]);
         tmem_ld_wait();
+        if (p.wide) {
+          // 32-byte aligned rows: ONE 256-bit store per (frame, direction) row - st.global.v8.f32 reaches 4.3 TB/s on 32-byte row pieces where
+          // two 16-byte stores of a lane pair reach 1.8 (tools/ubench/scatter_store3.cu).  The Re lane writes the even frame of a pair, the
+          // Im lane the odd one; each hands the other its four bins of the frame it does not write.
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const long long t = (long long)tt * FT_BM + fh * 64 + j * 8 + i;
-          const float v0 = __uint_as_float(r[0][i]) * p.out_scale, v1 = __uint_as_float(r[1][i]) * p.out_scale;
-          const float v2 = __uint_as_float(r[2][i]) * p.out_scale, v3 = __uint_as_float(r[3][i]) * p.out_scale;
-          // even lane (Re) lacks Im of bins 0, 1 and gives Re of bins 2, 3; odd lane (Im) the other way round
-          const float g0 = __shfl_xor_sync(0xffffffffu, odd ? v0 : v2, 1), g1 = __shfl_xor_sync(0xffffffffu, odd ? v1 : v3, 1);
-          const float4 o = odd ? make_float4(g0, v2, g1, v3) : make_float4(v0, g0, v1, g1);
-          if (store && t < p.BT) *reinterpret_cast<float4 *>(col + (size_t)t * p.D * p.KP) = o;
+          for (int i = 0; i < 8; i += 2) {
+            float mine[4], give[4], got[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const float ve = __uint_as_float(r[b][i]) * p.out_scale, vo = __uint_as_float(r[b][i + 1]) * p.out_scale;
+              mine[b] = odd ? vo : ve;
+              give[b] = odd ? ve : vo;
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) got[b] = __shfl_xor_sync(0xffffffffu, give[b], 1);
+            const long long t = (long long)tt * FT_BM + fh * 64 + j * 8 + i + (odd ? 1 : 0);
+            if (d < p.D && t < p.BT) {
+              float2 *dst = col + (size_t)t * p.D * p.KPo;
+              if (odd) st_global_v8(dst, got[0], mine[0], got[1], mine[1], got[2], mine[2], got[3], mine[3]);
+              else st_global_v8(dst, mine[0], got[0], mine[1], got[1], mine[2], got[2], mine[3], got[3]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const long long t = (long long)tt * FT_BM + fh * 64 + j * 8 + i;
+            const float v0 = __uint_as_float(r[0][i]) * p.out_scale, v1 = __uint_as_float(r[1][i]) * p.out_scale;
+            const float v2 = __uint_as_float(r[2][i]) * p.out_scale, v3 = __uint_as_float(r[3][i]) * p.out_scale;
+            // even lane (Re) lacks Im of bins 0, 1 and gives Re of bins 2, 3; odd lane (Im) the other way round
+            const float g0 = __shfl_xor_sync(0xffffffffu, odd ? v0 : v2, 1), g1 = __shfl_xor_sync(0xffffffffu, odd ? v1 : v3, 1);
+            const float4 o = odd ? make_float4(g0, v2, g1, v3) : make_float4(v0, g0, v1, g1);
+            if (store && t < p.BT) *reinterpret_cast<float4 *>(col + (size_t)t * p.D * p.KPo) = o;
+          }
         }
       }
       tc_fence_before();
@@ -256,11 +281,16 @@ bool k_ds_fan_tensor_supported(int M) { return M % 16 == 0 && M >= 16 && M <= 64
 
 // Supported shapes: M in {16, 32, 48, 64}; anything else runs the CUDA-core tile kernel (still on the GPU).  The spectra's pad bin
 // (index N/2 + 1) must be zero, as every producer of spectra in this library leaves it: it comes out as the beams' pad bin.
-int k_ds_fan_tensor(const float2 *spec, int B, int T, int M, int N, const uint64_t *steer_fx, int D, float2 *out, cudaStream_t st) {
+int k_ds_fan_tensor(const float2 *spec, int B, int T, int M, int N, const uint64_t *steer_fx, int D, float2 *out, cudaStream_t st, int out_pitch) {
   if (B <= 0 || T <= 0 || D <= 0) return 0;
-  if (!k_ds_fan_tensor_supported(M)) return k_ds_fan(spec, B, T, M, N, steer_fx, D, out, st);
+  if (!k_ds_fan_tensor_supported(M)) return k_ds_fan(spec, B, T, M, N, steer_fx, D, out, st, out_pitch);
   FtParams p;
   p.spec = spec; p.beams = out; p.BT = (long long)B * T; p.D = D; p.M = M; p.K = N / 2 + 1; p.KP = spec_pitch(N);
+  p.KPo = out_pitch > 0 ? out_pitch : p.KP;
+  if (p.KPo < p.KP) return mcag_set_error(1, "ds_fan_tensor: output pitch below the spectrum pitch");
+  // rows that start on 32-byte boundaries and hold whole four-bin groups: the 256-bit store path (fan_out_pitch(N) rows of MCAG_KIND_DSFAN)
+  p.wide = ((p.KPo & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0) ? 1 : 0;
+  if (!p.wide && p.KPo != p.KP) return mcag_set_error(1, "ds_fan_tensor: a padded output pitch must be a multiple of 4 bins on a 32-byte aligned buffer");
   p.n_tt = (int)((p.BT + FT_BM - 1) / FT_BM); p.n_dt = (D + FT_BD - 1) / FT_BD; p.n_kg = (p.KP + FT_NB - 1) / FT_NB;
   p.steer_fx = steer_fx; p.out_scale = 1.0f / (float)M;
   int dev = 0, sms = 148;
@@ -285,5 +315,5 @@ int k_ds_fan_tensor(const float2 *spec, int B, int T, int M, int N, const uint64
 }  // namespace mcag
 
 extern "C" int mcag_k_ds_fan_tensor(const void *d_spec, int B, int T, int M, int N, const uint64_t *d_steer_fx, int D, void *d_out, void *stream) {
-  return mcag::k_ds_fan_tensor((const float2 *)d_spec, B, T, M, N, d_steer_fx, D, (float2 *)d_out, (cudaStream_t)stream);
+  return mcag::k_ds_fan_tensor((const float2 *)d_spec, B, T, M, N, d_steer_fx, D, (float2 *)d_out, (cudaStream_t)stream, 0);
 }

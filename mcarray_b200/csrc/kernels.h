@@ -42,8 +42,9 @@ int k_curve_scan_argmax(const float *corr, int B, int T, int D, float mem, float
 int k_steer_table(const uint64_t *fx, int DM, int N, float2 *tab, cudaStream_t st);
 int k_ds_select(const float2 *spec, int B, int T, int M, int N, const float2 *steer_tab, const int32_t *cells, int S, int C_out, float2 *out,
                 cudaStream_t st);
-int k_ds_fan(const float2 *spec, int B, int T, int M, int N, const uint64_t *steer_fx, int D, float2 *out, cudaStream_t st);
-int k_fs_fan(const float2 *spec, int B, int T, int M, int N, const float2 *weights /* [D][M][KP] */, int D, float2 *out, cudaStream_t st);
+// out_pitch: complex bins per output row (0 = the spectrum pitch N/2 + 2); bins past N/2 are written as zeros
+int k_ds_fan(const float2 *spec, int B, int T, int M, int N, const uint64_t *steer_fx, int D, float2 *out, cudaStream_t st, int out_pitch = 0);
+int k_fs_fan(const float2 *spec, int B, int T, int M, int N, const float2 *weights /* [D][M][KP] */, int D, float2 *out, cudaStream_t st, int out_pitch = 0);
 
 // srp.cu
 int k_srp_channel(const float2 *spec, int B, int T, int M, int N, const uint64_t *mic_fx, int D, float *srp, cudaStream_t st);
@@ -57,7 +58,8 @@ int k_srp_tensor(const float2 *spec, int B, int T, int M, int N, const uint64_t 
 
 // fan_tc.cu (tcgen05): the delay-and-sum fan, four bins of a (frame, direction) tile resident in TMEM
 bool k_ds_fan_tensor_supported(int M);
-int k_ds_fan_tensor(const float2 *spec, int B, int T, int M, int N, const uint64_t *steer_fx, int D, float2 *out, cudaStream_t st);
+int k_ds_fan_tensor(const float2 *spec, int B, int T, int M, int N, const uint64_t *steer_fx, int D, float2 *out, cudaStream_t st, int out_pitch = 0);
+inline int fan_out_pitch(int N) { return (N / 2 + 2 + 3) & ~3; }   // beams rows of MCAG_KIND_DSFAN: 32-byte aligned (256-bit stores)
 
 // mask.cu
 int k_mask_stats(const float2 *spec, long long BT, int N, const float *H2, int nb, float *stats, cudaStream_t st);

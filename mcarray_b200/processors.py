@@ -362,7 +362,7 @@ class DelayAndSumFan(Processor):
 
     def beams(self):
         B, T = self._bt()
-        return self.fetch(capi.OUT_BEAMS, (B, T, self.info.n_dirs, self.info.spectrum_pitch))[..., : self.info.one_sided_length]
+        return self.fetch(capi.OUT_BEAMS, (B, T, self.info.n_dirs, self.info.beams_pitch))[..., : self.info.one_sided_length]
 
 
 class FilterAndSumFan(Processor):
@@ -378,7 +378,7 @@ class FilterAndSumFan(Processor):
 
     def beams(self):
         B, T = self._bt()
-        return self.fetch(capi.OUT_BEAMS, (B, T, self.info.n_dirs, self.info.spectrum_pitch))[..., : self.info.one_sided_length]
+        return self.fetch(capi.OUT_BEAMS, (B, T, self.info.n_dirs, self.info.beams_pitch))[..., : self.info.one_sided_length]
 
 
 class SrpPhat(Processor):
