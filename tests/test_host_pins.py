@@ -94,3 +94,18 @@ def test_ds_fan_oracle_reduces_to_the_reference_beamformer(orc, ref_available, n
             for d, doa in enumerate(doas):
                 one = orc.beamformer_frame(fs, xyz, ccs[t], doa, prefix=prefix)
                 assert np.array_equal(np.ascontiguousarray(fan[t, d]).view(np.float64), one), (prefix, t, d)
+
+
+def test_kernel_schedule_prototypes():
+    """the numpy restatements of the two register-resident transform schedules the CUDA kernels implement (tools/proto): the half-warp
+    real FFT of fft16.cuh for both sizes, and the decimated inverse transform of the warp-synchronous lag phase (tdoa_warp.cuh)"""
+    import glob
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    scripts = sorted(glob.glob(os.path.join(root, "tools", "proto", "*.py")))
+    assert scripts
+    for s in scripts:
+        r = subprocess.run([sys.executable, s], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (s, r.stdout[-500:], r.stderr[-500:])
