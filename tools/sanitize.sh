@@ -33,6 +33,6 @@ for p, x in ((mb.SourceSeparationAndLocalisation(fs, xyz4, 1, usePowerFloor=Fals
     p.synchronize(); p.close()
 print("sanitizer workload done")
 PY
-for tool in memcheck racecheck; do
+for tool in memcheck racecheck synccheck; do
   echo "== $tool"; timeout 900 compute-sanitizer --tool $tool --print-limit 5 python /tmp/san.py 2>&1 | tail -8
 done
